@@ -1,0 +1,150 @@
+/* lcpb200.h -- C ABI of the B200-native batched LCP contact solver.
+ *
+ * The reference (locuslab/lcp-physics) is pure Python and has no FFI; this
+ * header is the boundary a maintainer binds with ctypes.
+ * Every entry point replaces a reference interface on the hot path
+ * (paths relative to the reference tree):
+ *
+ *   lcpb200_forward          lcp_physics/lcp/lcp.py:22-35   LCPFunction.forward
+ *                            = lcp/solvers/pdipm.py:357-408 pre_factor_kkt
+ *                            + lcp/solvers/pdipm.py:49-179  forward (PDIPM loop)
+ *                            + pdipm.py:414-454 factor_kkt, :325-354 solve_kkt,
+ *                              :182-186 get_step
+ *   lcpb200_backward         lcp_physics/lcp/lcp.py:37-64   LCPFunction.backward
+ *   lcpb200_assemble         lcp_physics/physics/world.py:144-234 (M,Jc,Jf,E,mu,
+ *                            restitutions) + physics/engines.py:50-74 (G,F,h,p)
+ *   lcpb200_assemble_backward  autograd through the same assembly
+ *   lcpb200_forward_host / lcpb200_backward_host
+ *                            the same calls with HOST buffers (pinned or
+ *                            pageable); H2D/D2H copies are done inside, chunked
+ *                            and overlapped with the kernels.
+ *
+ * Conventions
+ *   - All matrices are dense, row-major, batch-major and contiguous, exactly
+ *     the tensors LCPFunction receives: Q[B,n,n] p[B,n] G[B,m,n] h[B,m]
+ *     A[B,e,n] b[B,e] F[B,m,m].  e == 0  <=>  A == b == NULL
+ *     (the reference passes 1-D empty tensors, engines.py:59-60).
+ *   - dtype: LCPB200_F32 or LCPB200_F64; all floating buffers share it.
+ *   - Device pointers unless the function name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void*; NULL = legacy default stream.
+ *   - Return value 0 = OK; non-zero = error, text via lcpb200_last_error_string().
+ *     No exceptions cross the ABI.  Per-scene solver status is reported in
+ *     `status[B]` (see LCPB200_STATUS_*): a singular Q sets
+ *     LCPB200_STATUS_SINGULAR_Q and the caller raises the reference's
+ *     RuntimeError (pdipm.py:361-368).
+ *   - Scenes are independent: per-scene termination and per-scene get_step
+ *     maximum (<= 1.5e-12 rel from the batch-coupled reference).
+ *   - Factorisations are pivot-free, as the reference's own CUDA path
+ *     (pdipm.py:18 `pivot=not x.is_cuda`).
+ *   - One stream at a time per handle (the handle owns the workspace).
+ */
+#ifndef LCPB200_H
+#define LCPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCPB200_VERSION 100
+
+#define LCPB200_F32 0
+#define LCPB200_F64 1
+
+/* per-scene status written by lcpb200_forward */
+#define LCPB200_STATUS_MAX_ITER      0  /* ran all max_iter iterations            */
+#define LCPB200_STATUS_NOT_IMPROVED  1  /* not_improved_lim non-improving iters   */
+#define LCPB200_STATUS_CONVERGED     2  /* best residual < eps                    */
+#define LCPB200_STATUS_DIVERGED      3  /* mu > 1e100                             */
+#define LCPB200_STATUS_SINGULAR_Q   -1  /* zero / non-finite pivot factoring Q    */
+
+/* flags for lcpb200_backward */
+#define LCPB200_BWD_BUG_COMPATIBLE   0u /* reference behaviour: un-transposed KKT */
+#define LCPB200_BWD_EXACT_ADJOINT    1u /* transposed KKT system (true adjoint)                  */
+
+typedef struct lcpb200_handle_s* lcpb200_handle_t;
+
+int         lcpb200_version(void);
+const char* lcpb200_last_error_string(void);
+
+/* Create a solver for problems of size (n, m, e) in `dtype` on CUDA device
+ * `device`. The handle owns a small per-CTA workspace (independent of B). */
+int lcpb200_create(int dtype, int n, int m, int e, int device, lcpb200_handle_t* out);
+int lcpb200_destroy(lcpb200_handle_t h);
+size_t lcpb200_workspace_bytes(lcpb200_handle_t h);
+/* Describe the launch plan (threads, dynamic smem, grid, which matrices are
+ * smem-resident) into `buf` -- for logs and DESIGN.md. */
+int lcpb200_describe(lcpb200_handle_t h, char* buf, size_t len);
+
+/* LCPFunction.forward. Outputs: zhat[B,n], nu[B,e] (NULL if e==0), lam[B,m],
+ * slack[B,m], status[B] int32, iters[B] int32 (PDIPM iterations executed),
+ * resid[B] (best residual, same dtype; may be NULL). */
+int lcpb200_forward(lcpb200_handle_t h, int B,
+                    const void* Q, const void* p, const void* G, const void* hvec,
+                    const void* A, const void* b, const void* F,
+                    double eps, int not_improved_lim, int max_iter,
+                    void* zhat, void* nu, void* lam, void* slack,
+                    int32_t* status, int32_t* iters, void* resid,
+                    void* stream);
+
+/* LCPFunction.backward. Inputs: the forward inputs it needs (Q,G,A,F), the
+ * saved forward results (zhat, nu, lam, slack) and dl_dzhat[B,n].
+ * Outputs (any may be NULL = skip): dQ[B,n,n] dp[B,n] dG[B,m,n] dh[B,m]
+ * dA[B,e,n] db[B,e] dF[B,m,m]. */
+int lcpb200_backward(lcpb200_handle_t h, int B,
+                     const void* Q, const void* G, const void* A, const void* F,
+                     const void* zhat, const void* nu, const void* lam, const void* slack,
+                     const void* dl_dzhat,
+                     void* dQ, void* dp, void* dG, void* dh, void* dA, void* db, void* dF,
+                     unsigned flags, void* stream);
+
+/* Same two calls with HOST buffers: copies in, solves, copies out. The timed
+ * "e2e" path of bench.py. Synchronous on return. */
+int lcpb200_forward_host(lcpb200_handle_t h, int B,
+                         const void* Q, const void* p, const void* G, const void* hvec,
+                         const void* A, const void* b, const void* F,
+                         double eps, int not_improved_lim, int max_iter,
+                         void* zhat, void* nu, void* lam, void* slack,
+                         int32_t* status, int32_t* iters, void* resid);
+int lcpb200_backward_host(lcpb200_handle_t h, int B,
+                          const void* Q, const void* G, const void* A, const void* F,
+                          const void* zhat, const void* nu, const void* lam, const void* slack,
+                          const void* dl_dzhat,
+                          void* dQ, void* dp, void* dG, void* dh, void* dA, void* db, void* dF,
+                          unsigned flags);
+
+/* Contact-list -> dense LCP assembly for B scenes of nb bodies (3 dofs each,
+ * n = 3 nb), nc contacts, fd = 2 friction directions (world.py:191-192),
+ * m = nc (2 + fd). Structure-of-arrays inputs:
+ *   mass[B,nb] inertia[B,nb] v[B,n] fext[B,n]           bodies
+ *   normal[B,nc,2] p1[B,nc,2] p2[B,nc,2]                contact geometry
+ *   body1[nc] body2[nc] int32 (shared by the batch)     contact topology
+ *   mu[B,nc] restitution[B,nc]                          contact material
+ * Outputs: Q[B,n,n] p[B,n] G[B,m,n] h[B,m] F[B,m,m]  with
+ *   p = M v + dt fext,  h = [(Jc v) restitution, 0, 0]  (engines.py:32,53,74). */
+int lcpb200_assemble(int dtype, int B, int nb, int nc, double dt,
+                     const void* mass, const void* inertia, const void* v, const void* fext,
+                     const void* normal, const void* p1, const void* p2,
+                     const int32_t* body1, const int32_t* body2,
+                     const void* mu, const void* restitution,
+                     void* Q, void* p, void* G, void* hvec, void* F, void* stream);
+
+/* Adjoint of lcpb200_assemble: given dQ dp dG dh dF, accumulate gradients
+ * w.r.t. mass, inertia, v, fext, normal, p1, p2, mu, restitution (any NULL = skip). */
+int lcpb200_assemble_backward(int dtype, int B, int nb, int nc, double dt,
+                              const void* mass, const void* inertia, const void* v,
+                              const void* normal, const void* p1, const void* p2,
+                              const int32_t* body1, const int32_t* body2,
+                              const void* mu, const void* restitution,
+                              const void* dQ, const void* dp, const void* dG,
+                              const void* dh, const void* dF,
+                              void* dmass, void* dinertia, void* dv, void* dfext,
+                              void* dnormal, void* dp1, void* dp2,
+                              void* dmu, void* drestitution, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCPB200_H */

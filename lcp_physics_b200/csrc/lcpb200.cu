@@ -1,0 +1,432 @@
+// lcpb200.cu -- C ABI (include/lcpb200.h), launch planning, host-buffer pipeline.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/lcpb200.h"
+#include "lcp_assemble.cuh"
+#include "lcp_solver.cuh"
+
+using namespace lcpb200;
+
+static thread_local std::string g_err;
+static int fail(const std::string& s) { g_err = s; return 1; }
+#define CK(call)                                                                                 \
+  do {                                                                                           \
+    cudaError_t _e = (call);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" +      \
+                  std::to_string(__LINE__) + ")");                                               \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct lcpb200_handle_s {
+  int dtype, n, m, e, device;
+  int num_sms, smem_optin;
+  Plan plan;
+  int max_grid;            // resident CTAs (occupancy * SMs)
+  static const int NSLOT = 2;   // independent workspace slices (one per pipeline stream)
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  // host-buffer pipeline state
+  cudaStream_t streams[NSLOT] = {nullptr, nullptr};
+  DevBuf d_in[7], d_out[6], d_bwd[16];
+};
+
+template <typename T>
+static int make_plan(lcpb200_handle_s* h) {
+  Plan& P = h->plan;
+  const int n = h->n, m = h->m, e = h->e;
+  memset(&P, 0, sizeof(P));
+  P.n = n; P.m = m; P.e = e;
+  P.nt = (m >= 96 || n >= 96) ? 512 : (m >= 32 ? 256 : 128);
+  Vecs<T> vv;
+  const long long vec_elems = vv.carve(nullptr, n, m, e, P.nt);
+  long long budget = (long long)h->smem_optin - 1024 - vec_elems * (long long)sizeof(T);
+  if (budget < 0) return fail("problem too large: the shared-memory vectors alone exceed the per-CTA limit");
+  long long off = 0;
+  auto al4 = [](long long x) { return (x + 3) & ~3LL; };
+  P.ldT = m | 1;
+  P.ldG = n;
+  P.ldQi = n | 1;
+  const long long Tb = al4((long long)m * P.ldT), Gb = al4((long long)m * P.ldG), Qb = al4((long long)n * P.ldQi);
+  if (Tb * (long long)sizeof(T) <= budget) { P.T_smem = 1; P.off_T = (int)off; off += Tb; budget -= Tb * sizeof(T); }
+  if (Gb * (long long)sizeof(T) <= budget) { P.G_smem = 1; P.off_G = (int)off; off += Gb; budget -= Gb * sizeof(T); }
+  if (Qb * (long long)sizeof(T) <= budget) { P.Qi_smem = 1; P.off_Qi = (int)off; off += Qb; budget -= Qb * sizeof(T); }
+  P.off_vec = (int)off;
+  P.smem_bytes = (int)((off + vec_elems) * sizeof(T));
+  long long w = 0;
+  P.w_Qi = w; w += Qb;
+  P.w_R = w; w += al4((long long)m * m);
+  P.w_T = w; w += Tb;
+  P.w_X = w; w += al4((long long)n * m);
+  P.w_XA = w; w += al4((long long)n * e);
+  P.w_S11 = w; w += al4((long long)e * e);
+  P.w_V = w; w += al4((long long)m * e);
+  P.w_W = w; w += al4((long long)e * m);
+  P.ws_per_cta = w;
+  return 0;
+}
+
+template <typename T>
+static int configure_kernels(lcpb200_handle_s* h) {
+  const Plan& P = h->plan;
+  // The attribute is per kernel, not per handle: always raise it to the device maximum so that
+  // handles with different plans can coexist.
+  const int dyn_max = h->smem_optin - 1024;
+  CK(cudaFuncSetAttribute(lcp_forward_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+  CK(cudaFuncSetAttribute(lcp_backward_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+  int occ_f = 0, occ_b = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, lcp_forward_kernel<T>, P.nt, P.smem_bytes));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, lcp_backward_kernel<T>, P.nt, P.smem_bytes));
+  int occ = std::min(occ_f, occ_b);
+  if (occ < 1) return fail("kernel cannot be resident with the planned shared memory");
+  occ = std::min(occ, 8);
+  h->max_grid = occ * h->num_sms;
+  h->plan.grid = h->max_grid;
+  return 0;
+}
+
+extern "C" int lcpb200_version(void) { return LCPB200_VERSION; }
+extern "C" const char* lcpb200_last_error_string(void) { return g_err.c_str(); }
+
+extern "C" int lcpb200_create(int dtype, int n, int m, int e, int device, lcpb200_handle_t* out) {
+  if (!out) return fail("out == NULL");
+  *out = nullptr;
+  if (dtype != LCPB200_F32 && dtype != LCPB200_F64) return fail("dtype must be LCPB200_F32 or LCPB200_F64");
+  if (n <= 0 || m <= 0 || e < 0) return fail("need n > 0, m > 0, e >= 0");
+  CK(cudaSetDevice(device));
+  lcpb200_handle_s* h = new (std::nothrow) lcpb200_handle_s();
+  if (!h) return fail("out of host memory");
+  h->dtype = dtype; h->n = n; h->m = m; h->e = e; h->device = device;
+  cudaError_t ce;
+  if ((ce = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess ||
+      (ce = cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess) {
+    delete h;
+    return fail(std::string("cudaDeviceGetAttribute: ") + cudaGetErrorString(ce));
+  }
+  int rc = (dtype == LCPB200_F32) ? make_plan<float>(h) : make_plan<double>(h);
+  if (!rc) rc = (dtype == LCPB200_F32) ? configure_kernels<float>(h) : configure_kernels<double>(h);
+  if (rc) { delete h; return rc; }
+  const size_t esz = dtype == LCPB200_F32 ? 4 : 8;
+  h->ws_bytes = (size_t)h->plan.ws_per_cta * esz * (size_t)h->max_grid * lcpb200_handle_s::NSLOT;
+  ce = cudaMalloc(&h->ws, h->ws_bytes);
+  if (ce != cudaSuccess) { delete h; return fail(std::string("cudaMalloc(workspace): ") + cudaGetErrorString(ce)); }
+  *out = h;
+  return 0;
+}
+
+extern "C" int lcpb200_destroy(lcpb200_handle_t h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  if (h->ws) cudaFree(h->ws);
+  for (auto& s : h->streams) if (s) cudaStreamDestroy(s);
+  for (auto& b : h->d_in) b.release();
+  for (auto& b : h->d_out) b.release();
+  for (auto& b : h->d_bwd) b.release();
+  delete h;
+  return 0;
+}
+
+extern "C" size_t lcpb200_workspace_bytes(lcpb200_handle_t h) { return h ? h->ws_bytes : 0; }
+
+extern "C" int lcpb200_describe(lcpb200_handle_t h, char* buf, size_t len) {
+  if (!h || !buf) return fail("null argument");
+  const Plan& P = h->plan;
+  snprintf(buf, len,
+           "dtype=%s n=%d m=%d e=%d threads=%d smem=%dB (T:%s G:%s Qinv:%s) ldT=%d grid<=%d "
+           "ws/CTA=%lldB sms=%d",
+           h->dtype == LCPB200_F32 ? "f32" : "f64", P.n, P.m, P.e, P.nt, P.smem_bytes,
+           P.T_smem ? "smem" : "L2", P.G_smem ? "smem" : "L2", P.Qi_smem ? "smem" : "L2", P.ldT,
+           h->max_grid, (long long)(P.ws_per_cta * (h->dtype == LCPB200_F32 ? 4 : 8)), h->num_sms);
+  return 0;
+}
+
+template <typename T>
+static int launch_forward(lcpb200_handle_s* h, int slot, int B, const void* Q, const void* p, const void* G,
+                          const void* hv, const void* A, const void* b, const void* F, double eps,
+                          int not_improved_lim, int max_iter, void* zhat, void* nu, void* lam, void* slack,
+                          int32_t* status, int32_t* iters, void* resid, cudaStream_t st) {
+  FwdArgs<T> a;
+  a.P = h->plan;
+  a.B = B;
+  a.Q = (const T*)Q; a.p = (const T*)p; a.G = (const T*)G; a.h = (const T*)hv;
+  a.A = (const T*)A; a.b = (const T*)b; a.F = (const T*)F;
+  a.zhat = (T*)zhat; a.nu = (T*)nu; a.lam = (T*)lam; a.slack = (T*)slack; a.resid = (T*)resid;
+  a.status = status; a.iters = iters;
+  a.eps = (T)eps; a.not_improved_lim = not_improved_lim; a.max_iter = max_iter;
+  a.ws = (T*)h->ws + (size_t)slot * h->plan.ws_per_cta * h->max_grid;
+  const int grid = std::min(B, h->max_grid);
+  lcp_forward_kernel<T><<<grid, h->plan.nt, h->plan.smem_bytes, st>>>(a);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+static int launch_backward(lcpb200_handle_s* h, int slot, int B, const void* Q, const void* G, const void* A,
+                           const void* F, const void* zhat, const void* nu, const void* lam, const void* slack,
+                           const void* g, void* dQ, void* dp, void* dG, void* dh, void* dA, void* db, void* dF,
+                           unsigned flags, cudaStream_t st) {
+  BwdArgs<T> a;
+  a.P = h->plan;
+  a.B = B;
+  a.Q = (const T*)Q; a.G = (const T*)G; a.A = (const T*)A; a.F = (const T*)F;
+  a.zhat = (const T*)zhat; a.nu = (const T*)nu; a.lam = (const T*)lam; a.slack = (const T*)slack;
+  a.g = (const T*)g;
+  a.dQ = (T*)dQ; a.dp = (T*)dp; a.dG = (T*)dG; a.dh = (T*)dh; a.dA = (T*)dA; a.db = (T*)db; a.dF = (T*)dF;
+  a.flags = flags;
+  a.ws = (T*)h->ws + (size_t)slot * h->plan.ws_per_cta * h->max_grid;
+  const int grid = std::min(B, h->max_grid);
+  lcp_backward_kernel<T><<<grid, h->plan.nt, h->plan.smem_bytes, st>>>(a);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int check_fwd_args(lcpb200_handle_t h, int B, const void* Q, const void* p, const void* G, const void* hv,
+                          const void* A, const void* b, const void* F, const void* zhat, const void* nu,
+                          const void* lam, const void* slack, const void* status, const void* iters,
+                          int max_iter) {
+  if (!h) return fail("null handle");
+  if (B < 0) return fail("B < 0");
+  if (!Q || !p || !G || !hv || !F) return fail("Q, p, G, h, F must be non-NULL");
+  if (h->e > 0 && (!A || !b)) return fail("handle was created with e > 0 but A or b is NULL");
+  if (!zhat || !lam || !slack || !status || !iters) return fail("zhat, lam, slack, status, iters must be non-NULL");
+  if (h->e > 0 && !nu) return fail("nu must be non-NULL when e > 0");
+  if (max_iter < 0) return fail("max_iter < 0");
+  return 0;
+}
+
+extern "C" int lcpb200_forward(lcpb200_handle_t h, int B, const void* Q, const void* p, const void* G,
+                               const void* hv, const void* A, const void* b, const void* F, double eps,
+                               int not_improved_lim, int max_iter, void* zhat, void* nu, void* lam, void* slack,
+                               int32_t* status, int32_t* iters, void* resid, void* stream) {
+  if (int rc = check_fwd_args(h, B, Q, p, G, hv, A, b, F, zhat, nu, lam, slack, status, iters, max_iter)) return rc;
+  if (B == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  return h->dtype == LCPB200_F32
+             ? launch_forward<float>(h, 0, B, Q, p, G, hv, A, b, F, eps, not_improved_lim, max_iter, zhat, nu, lam,
+                                     slack, status, iters, resid, st)
+             : launch_forward<double>(h, 0, B, Q, p, G, hv, A, b, F, eps, not_improved_lim, max_iter, zhat, nu, lam,
+                                      slack, status, iters, resid, st);
+}
+
+extern "C" int lcpb200_backward(lcpb200_handle_t h, int B, const void* Q, const void* G, const void* A,
+                                const void* F, const void* zhat, const void* nu, const void* lam,
+                                const void* slack, const void* g, void* dQ, void* dp, void* dG, void* dh, void* dA,
+                                void* db, void* dF, unsigned flags, void* stream) {
+  if (!h) return fail("null handle");
+  if (B < 0) return fail("B < 0");
+  if (!Q || !G || !F || !zhat || !lam || !slack || !g) return fail("Q, G, F, zhat, lam, slack, dl_dzhat must be non-NULL");
+  if (h->e > 0 && (!A || !nu)) return fail("A and nu must be non-NULL when e > 0");
+  if (flags != LCPB200_BWD_BUG_COMPATIBLE)
+    return fail("only LCPB200_BWD_BUG_COMPATIBLE is implemented (the reference's backward, lcp.py:37-64)");
+  if (B == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  return h->dtype == LCPB200_F32
+             ? launch_backward<float>(h, 0, B, Q, G, A, F, zhat, nu, lam, slack, g, dQ, dp, dG, dh, dA, db, dF, flags, st)
+             : launch_backward<double>(h, 0, B, Q, G, A, F, zhat, nu, lam, slack, g, dQ, dp, dG, dh, dA, db, dF, flags, st);
+}
+
+// ------------------------------------------------------------------ host-buffer pipeline
+// Chunks of scenes are copied in on one of two streams, solved on the same stream and copied
+// back, so the H2D copy of chunk k+1 overlaps the solve of chunk k (each stream has its own
+// workspace slice).
+static int ensure_streams(lcpb200_handle_s* h) {
+  for (auto& s : h->streams)
+    if (!s) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  return 0;
+}
+
+static int chunk_scenes(const lcpb200_handle_s* h, int B) {
+  // at least two waves of CTAs per chunk, at most 8 chunks
+  int c = std::max(2 * h->max_grid, (B + 7) / 8);
+  return std::max(1, std::min(c, B));
+}
+
+extern "C" int lcpb200_forward_host(lcpb200_handle_t h, int B, const void* Q, const void* p, const void* G,
+                                    const void* hv, const void* A, const void* b, const void* F, double eps,
+                                    int not_improved_lim, int max_iter, void* zhat, void* nu, void* lam,
+                                    void* slack, int32_t* status, int32_t* iters, void* resid) {
+  if (int rc = check_fwd_args(h, B, Q, p, G, hv, A, b, F, zhat, nu, lam, slack, status, iters, max_iter)) return rc;
+  if (B == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  if (int rc = ensure_streams(h)) return rc;
+  const size_t w = h->dtype == LCPB200_F32 ? 4 : 8;
+  const size_t n = h->n, m = h->m, e = h->e;
+  const size_t in_sz[7] = {n * n * w, n * w, m * n * w, m * w, e * n * w, e * w, m * m * w};
+  const void* in_src[7] = {Q, p, G, hv, A, b, F};
+  const size_t out_sz[6] = {n * w, e * w, m * w, m * w, 4, 4};
+  void* out_dst[6] = {zhat, nu, lam, slack, status, iters};
+  for (int i = 0; i < 7; ++i) if (in_sz[i]) CK(h->d_in[i].ensure(in_sz[i] * B));
+  for (int i = 0; i < 6; ++i) if (out_sz[i]) CK(h->d_out[i].ensure(out_sz[i] * B));
+  DevBuf& d_resid = h->d_bwd[15];
+  if (resid) CK(d_resid.ensure(w * B));
+  const int C = chunk_scenes(h, B);
+  int k = 0;
+  for (int s0 = 0; s0 < B; s0 += C, ++k) {
+    const int cb = std::min(C, B - s0);
+    const int slot = k % lcpb200_handle_s::NSLOT;
+    cudaStream_t st = h->streams[slot];
+    for (int i = 0; i < 7; ++i)
+      if (in_sz[i] && in_src[i])
+        CK(cudaMemcpyAsync((char*)h->d_in[i].p + in_sz[i] * s0, (const char*)in_src[i] + in_sz[i] * s0,
+                           in_sz[i] * cb, cudaMemcpyHostToDevice, st));
+    auto at = [&](DevBuf& bf, size_t per) -> void* { return per ? (char*)bf.p + per * s0 : nullptr; };
+    int rc = h->dtype == LCPB200_F32
+                 ? launch_forward<float>(h, slot, cb, at(h->d_in[0], in_sz[0]), at(h->d_in[1], in_sz[1]),
+                                         at(h->d_in[2], in_sz[2]), at(h->d_in[3], in_sz[3]), at(h->d_in[4], in_sz[4]),
+                                         at(h->d_in[5], in_sz[5]), at(h->d_in[6], in_sz[6]), eps, not_improved_lim,
+                                         max_iter, at(h->d_out[0], out_sz[0]), at(h->d_out[1], out_sz[1]),
+                                         at(h->d_out[2], out_sz[2]), at(h->d_out[3], out_sz[3]),
+                                         (int32_t*)at(h->d_out[4], 4), (int32_t*)at(h->d_out[5], 4),
+                                         resid ? (char*)d_resid.p + w * s0 : nullptr, st)
+                 : launch_forward<double>(h, slot, cb, at(h->d_in[0], in_sz[0]), at(h->d_in[1], in_sz[1]),
+                                          at(h->d_in[2], in_sz[2]), at(h->d_in[3], in_sz[3]), at(h->d_in[4], in_sz[4]),
+                                          at(h->d_in[5], in_sz[5]), at(h->d_in[6], in_sz[6]), eps, not_improved_lim,
+                                          max_iter, at(h->d_out[0], out_sz[0]), at(h->d_out[1], out_sz[1]),
+                                          at(h->d_out[2], out_sz[2]), at(h->d_out[3], out_sz[3]),
+                                          (int32_t*)at(h->d_out[4], 4), (int32_t*)at(h->d_out[5], 4),
+                                          resid ? (char*)d_resid.p + w * s0 : nullptr, st);
+    if (rc) return rc;
+    for (int i = 0; i < 6; ++i)
+      if (out_sz[i] && out_dst[i])
+        CK(cudaMemcpyAsync((char*)out_dst[i] + out_sz[i] * s0, (char*)h->d_out[i].p + out_sz[i] * s0,
+                           out_sz[i] * cb, cudaMemcpyDeviceToHost, st));
+    if (resid)
+      CK(cudaMemcpyAsync((char*)resid + w * s0, (char*)d_resid.p + w * s0, w * cb, cudaMemcpyDeviceToHost, st));
+  }
+  for (auto& s : h->streams) CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int lcpb200_backward_host(lcpb200_handle_t h, int B, const void* Q, const void* G, const void* A,
+                                     const void* F, const void* zhat, const void* nu, const void* lam,
+                                     const void* slack, const void* g, void* dQ, void* dp, void* dG, void* dh,
+                                     void* dA, void* db, void* dF, unsigned flags) {
+  if (!h) return fail("null handle");
+  if (B < 0) return fail("B < 0");
+  if (!Q || !G || !F || !zhat || !lam || !slack || !g) return fail("Q, G, F, zhat, lam, slack, dl_dzhat must be non-NULL");
+  if (h->e > 0 && (!A || !nu)) return fail("A and nu must be non-NULL when e > 0");
+  if (flags != LCPB200_BWD_BUG_COMPATIBLE) return fail("only LCPB200_BWD_BUG_COMPATIBLE is implemented");
+  if (B == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  if (int rc = ensure_streams(h)) return rc;
+  const size_t w = h->dtype == LCPB200_F32 ? 4 : 8;
+  const size_t n = h->n, m = h->m, e = h->e;
+  // inputs: Q G A F zhat nu lam slack g ; outputs: dQ dp dG dh dA db dF
+  const size_t in_sz[9] = {n * n * w, m * n * w, e * n * w, m * m * w, n * w, e * w, m * w, m * w, n * w};
+  const void* in_src[9] = {Q, G, A, F, zhat, nu, lam, slack, g};
+  // Q, G, A, F may already be resident from forward_host (same buffers d_in[0,2,4,6]); we re-copy for safety.
+  DevBuf* in_buf[9] = {&h->d_in[0], &h->d_in[2], &h->d_in[4], &h->d_in[6], &h->d_bwd[0], &h->d_bwd[1],
+                       &h->d_bwd[2], &h->d_bwd[3], &h->d_bwd[4]};
+  const size_t out_sz[7] = {n * n * w, n * w, m * n * w, m * w, e * n * w, e * w, m * m * w};
+  void* out_dst[7] = {dQ, dp, dG, dh, dA, db, dF};
+  DevBuf* out_buf[7] = {&h->d_bwd[5], &h->d_bwd[6], &h->d_bwd[7], &h->d_bwd[8], &h->d_bwd[9], &h->d_bwd[10],
+                        &h->d_bwd[11]};
+  for (int i = 0; i < 9; ++i) if (in_sz[i] && in_src[i]) CK(in_buf[i]->ensure(in_sz[i] * B));
+  for (int i = 0; i < 7; ++i) if (out_sz[i] && out_dst[i]) CK(out_buf[i]->ensure(out_sz[i] * B));
+  const int C = chunk_scenes(h, B);
+  int k = 0;
+  for (int s0 = 0; s0 < B; s0 += C, ++k) {
+    const int cb = std::min(C, B - s0);
+    const int slot = k % lcpb200_handle_s::NSLOT;
+    cudaStream_t st = h->streams[slot];
+    for (int i = 0; i < 9; ++i)
+      if (in_sz[i] && in_src[i])
+        CK(cudaMemcpyAsync((char*)in_buf[i]->p + in_sz[i] * s0, (const char*)in_src[i] + in_sz[i] * s0,
+                           in_sz[i] * cb, cudaMemcpyHostToDevice, st));
+    auto ai = [&](int i) -> void* { return (in_sz[i] && in_src[i]) ? (char*)in_buf[i]->p + in_sz[i] * s0 : nullptr; };
+    auto ao = [&](int i) -> void* { return (out_sz[i] && out_dst[i]) ? (char*)out_buf[i]->p + out_sz[i] * s0 : nullptr; };
+    int rc = h->dtype == LCPB200_F32
+                 ? launch_backward<float>(h, slot, cb, ai(0), ai(1), ai(2), ai(3), ai(4), ai(5), ai(6), ai(7), ai(8),
+                                          ao(0), ao(1), ao(2), ao(3), ao(4), ao(5), ao(6), flags, st)
+                 : launch_backward<double>(h, slot, cb, ai(0), ai(1), ai(2), ai(3), ai(4), ai(5), ai(6), ai(7), ai(8),
+                                           ao(0), ao(1), ao(2), ao(3), ao(4), ao(5), ao(6), flags, st);
+    if (rc) return rc;
+    for (int i = 0; i < 7; ++i)
+      if (out_sz[i] && out_dst[i])
+        CK(cudaMemcpyAsync((char*)out_dst[i] + out_sz[i] * s0, (char*)out_buf[i]->p + out_sz[i] * s0,
+                           out_sz[i] * cb, cudaMemcpyDeviceToHost, st));
+  }
+  for (auto& s : h->streams) CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// ------------------------------------------------------------------ assembly
+extern "C" int lcpb200_assemble(int dtype, int B, int nb, int nc, double dt, const void* mass, const void* inertia,
+                                const void* v, const void* fext, const void* normal, const void* p1,
+                                const void* p2, const int32_t* body1, const int32_t* body2, const void* mu,
+                                const void* restitution, void* Q, void* p, void* G, void* hv, void* F,
+                                void* stream) {
+  if (dtype != LCPB200_F32 && dtype != LCPB200_F64) return fail("bad dtype");
+  if (B < 0 || nb <= 0 || nc <= 0) return fail("need B >= 0, nb > 0, nc > 0");
+  if (!mass || !inertia || !v || !fext || !normal || !p1 || !p2 || !body1 || !body2 || !mu || !restitution)
+    return fail("assemble: NULL input");
+  if (!Q || !p || !G || !hv || !F) return fail("assemble: NULL output");
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LCPB200_F32)
+    launch_assemble<float>(B, nb, nc, (float)dt, (const float*)mass, (const float*)inertia, (const float*)v,
+                           (const float*)fext, (const float*)normal, (const float*)p1, (const float*)p2, body1,
+                           body2, (const float*)mu, (const float*)restitution, (float*)Q, (float*)p, (float*)G,
+                           (float*)hv, (float*)F, st);
+  else
+    launch_assemble<double>(B, nb, nc, dt, (const double*)mass, (const double*)inertia, (const double*)v,
+                            (const double*)fext, (const double*)normal, (const double*)p1, (const double*)p2,
+                            body1, body2, (const double*)mu, (const double*)restitution, (double*)Q, (double*)p,
+                            (double*)G, (double*)hv, (double*)F, st);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int lcpb200_assemble_backward(int dtype, int B, int nb, int nc, double dt, const void* mass,
+                                         const void* inertia, const void* v, const void* normal, const void* p1,
+                                         const void* p2, const int32_t* body1, const int32_t* body2,
+                                         const void* mu, const void* restitution, const void* dQ, const void* dp,
+                                         const void* dG, const void* dh, const void* dF, void* dmass,
+                                         void* dinertia, void* dv, void* dfext, void* dnormal, void* dp1,
+                                         void* dp2, void* dmu, void* drestitution, void* stream) {
+  if (dtype != LCPB200_F32 && dtype != LCPB200_F64) return fail("bad dtype");
+  if (B < 0 || nb <= 0 || nc <= 0) return fail("need B >= 0, nb > 0, nc > 0");
+  if (!mass || !inertia || !v || !normal || !p1 || !p2 || !body1 || !body2 || !mu || !restitution)
+    return fail("assemble_backward: NULL input");
+  if (!dQ || !dp || !dG || !dh || !dF) return fail("assemble_backward: NULL upstream gradient");
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LCPB200_F32)
+    launch_assemble_backward<float>(B, nb, nc, (float)dt, (const float*)mass, (const float*)inertia,
+                                    (const float*)v, (const float*)normal, (const float*)p1, (const float*)p2,
+                                    body1, body2, (const float*)mu, (const float*)restitution, (const float*)dQ,
+                                    (const float*)dp, (const float*)dG, (const float*)dh, (const float*)dF,
+                                    (float*)dmass, (float*)dinertia, (float*)dv, (float*)dfext, (float*)dnormal,
+                                    (float*)dp1, (float*)dp2, (float*)dmu, (float*)drestitution, st);
+  else
+    launch_assemble_backward<double>(B, nb, nc, dt, (const double*)mass, (const double*)inertia, (const double*)v,
+                                     (const double*)normal, (const double*)p1, (const double*)p2, body1, body2,
+                                     (const double*)mu, (const double*)restitution, (const double*)dQ,
+                                     (const double*)dp, (const double*)dG, (const double*)dh, (const double*)dF,
+                                     (double*)dmass, (double*)dinertia, (double*)dv, (double*)dfext,
+                                     (double*)dnormal, (double*)dp1, (double*)dp2, (double*)dmu,
+                                     (double*)drestitution, st);
+  CK(cudaGetLastError());
+  return 0;
+}
