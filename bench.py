@@ -177,6 +177,7 @@ def run_b200(args, rank, world, local_rank):
                 torch.empty(B, M_INEQ, **kw), None, None, torch.empty(B, M_INEQ, M_INEQ, **kw))
 
     fo, bo = mk_fwd_out(dev), mk_bwd_out(dev)
+    saved = {"R_buffer": torch.empty(B, M_INEQ, M_INEQ, dtype=dtype, device=dev)}   # the reference's self.R (lcp.py:28)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kev = []
 
@@ -184,10 +185,10 @@ def run_b200(args, rank, world, local_rank):
         if record:
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record()
-        solve_forward(Q, p, G, h, A, b, F, max_iter=MAX_ITER, out=fo)
+        solve_forward(Q, p, G, h, A, b, F, max_iter=MAX_ITER, out=fo, save=saved)
         if record:
             e1.record()
-        solve_backward(Q, G, A, F, fo[0], None, fo[2], fo[3], g, out=bo)
+        solve_backward(Q, G, A, F, fo[0], None, fo[2], fo[3], g, out=bo, saved=saved)
         if record:
             e2.record()
             kev.append((e0, e1, e2))
@@ -229,9 +230,11 @@ def run_b200(args, rank, world, local_rank):
     hg = pin(g_host)
     hfo, hbo = mk_fwd_out("cpu", pin=True), mk_bwd_out("cpu", pin=True)
 
+    hsaved = {}
+
     def e2e_step():
-        solve_forward(*hin, max_iter=MAX_ITER, out=hfo)
-        solve_backward(hin[0], hin[2], hin[4], hin[6], hfo[0], None, hfo[2], hfo[3], hg, out=hbo)
+        solve_forward(*hin, max_iter=MAX_ITER, out=hfo, save=hsaved)
+        solve_backward(hin[0], hin[2], hin[4], hin[6], hfo[0], None, hfo[2], hfo[3], hg, out=hbo, saved=hsaved)
 
     e2e_steps = max(1, min(args.steps, 3))
     e2e_step()
@@ -246,8 +249,8 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = t.item()
     in_bytes = sum(t_.numel() * w for t_ in inp_host)
-    h2d = in_bytes + (N_DOF * N_DOF + M_INEQ * N_DOF + M_INEQ * M_INEQ) * w * B + (2 * N_DOF + 2 * M_INEQ) * w * B
-    d2h = ((N_DOF + 2 * M_INEQ + 1) * w + 8) * B + in_bytes
+    h2d = in_bytes + N_DOF * w * B                          # the 7 inputs once (kept on the device) + dl_dzhat
+    d2h = ((N_DOF + 2 * M_INEQ + 1) * w + 8) * B + in_bytes  # zhat, lam, slack, resid, status, iters + the 7 gradients
 
     if rank != 0:
         return

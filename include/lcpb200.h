@@ -78,15 +78,23 @@ size_t lcpb200_workspace_bytes(lcpb200_handle_t h);
  * smem-resident) into `buf` -- for logs and DESIGN.md. */
 int lcpb200_describe(lcpb200_handle_t h, char* buf, size_t len);
 
+/* Development aid: per-phase SM cycle counters of the solver kernels, summed over CTAs.
+ * enable=1 allocates/zeroes them, 0 frees; out (may be NULL) receives 6 values:
+ * {prefactor, load T, LU, KKT solves, residuals, step rules}. */
+int lcpb200_profile(lcpb200_handle_t h, int enable, long long* out);
+
 /* LCPFunction.forward. Outputs: zhat[B,n], nu[B,e] (NULL if e==0), lam[B,m],
  * slack[B,m], status[B] int32, iters[B] int32 (PDIPM iterations executed),
- * resid[B] (best residual, same dtype; may be NULL). */
+ * resid[B] (best residual, same dtype; may be NULL), Rsave[B,m,m] (may be NULL):
+ * the Schur matrix R = G Q^-1 G^T + F - ... of every scene (the `self.R` the
+ * reference keeps for backward, lcp.py:28); pass it to lcpb200_backward to skip
+ * the re-factorisation of Q and the Schur GEMM there. */
 int lcpb200_forward(lcpb200_handle_t h, int B,
                     const void* Q, const void* p, const void* G, const void* hvec,
                     const void* A, const void* b, const void* F,
                     double eps, int not_improved_lim, int max_iter,
                     void* zhat, void* nu, void* lam, void* slack,
-                    int32_t* status, int32_t* iters, void* resid,
+                    int32_t* status, int32_t* iters, void* resid, void* Rsave,
                     void* stream);
 
 /* LCPFunction.backward. Inputs: the forward inputs it needs (Q,G,A,F), the
@@ -98,10 +106,14 @@ int lcpb200_backward(lcpb200_handle_t h, int B,
                      const void* zhat, const void* nu, const void* lam, const void* slack,
                      const void* dl_dzhat,
                      void* dQ, void* dp, void* dG, void* dh, void* dA, void* db, void* dF,
+                     const void* Rsave /* from lcpb200_forward, or NULL = recompute */,
                      unsigned flags, void* stream);
 
 /* Same two calls with HOST buffers: copies in, solves, copies out. The timed
- * "e2e" path of bench.py. Synchronous on return. */
+ * "e2e" path of bench.py. Synchronous on return. forward_host leaves its inputs,
+ * results and R on the device; backward_host with Q == NULL (then G, A, F, zhat,
+ * nu, lam, slack are ignored) reuses them instead of uploading them again -- the
+ * save_for_backward of lcp.py:34. Any other call on the handle drops that state. */
 int lcpb200_forward_host(lcpb200_handle_t h, int B,
                          const void* Q, const void* p, const void* G, const void* hvec,
                          const void* A, const void* b, const void* F,

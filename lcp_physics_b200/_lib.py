@@ -24,9 +24,10 @@ _SIGS = {
     "lcpb200_destroy": (ctypes.c_int, [_vp]),
     "lcpb200_workspace_bytes": (ctypes.c_size_t, [_vp]),
     "lcpb200_describe": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_size_t]),
+    "lcpb200_profile": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]),
     "lcpb200_forward": (ctypes.c_int, [_vp, ctypes.c_int] + [_vp] * 7 +
-                        [ctypes.c_double, ctypes.c_int, ctypes.c_int] + [_vp] * 8),
-    "lcpb200_backward": (ctypes.c_int, [_vp, ctypes.c_int] + [_vp] * 16 + [ctypes.c_uint, _vp]),
+                        [ctypes.c_double, ctypes.c_int, ctypes.c_int] + [_vp] * 9),
+    "lcpb200_backward": (ctypes.c_int, [_vp, ctypes.c_int] + [_vp] * 17 + [ctypes.c_uint, _vp]),
     "lcpb200_forward_host": (ctypes.c_int, [_vp, ctypes.c_int] + [_vp] * 7 +
                              [ctypes.c_double, ctypes.c_int, ctypes.c_int] + [_vp] * 7),
     "lcpb200_backward_host": (ctypes.c_int, [_vp, ctypes.c_int] + [_vp] * 16 + [ctypes.c_uint]),
@@ -88,11 +89,18 @@ class Handle:
         self._h = _vp()
         check(lib.lcpb200_create(dtype_code(dtype), n, m, e, device_index, ctypes.byref(self._h)))
         self.key = (dtype, n, m, e, device_index)
+        self.host_generation = 0        # bumped by every host-buffer call (retained-state token)
 
     def describe(self):
         buf = ctypes.create_string_buffer(512)
         check(load().lcpb200_describe(self._h, buf, 512))
         return buf.value.decode()
+
+    def profile(self, enable=True):
+        """Read (then reset or disable) the per-phase cycle counters: dict name -> SM cycles."""
+        out = (ctypes.c_longlong * 6)()
+        check(load().lcpb200_profile(self._h, 1 if enable else 0, out))
+        return dict(zip(("prefactor", "load_T", "lu", "kkt_solve", "residual", "step"), list(out)))
 
     @property
     def raw(self):

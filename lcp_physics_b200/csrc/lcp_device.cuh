@@ -173,94 +173,109 @@ __device__ __forceinline__ void invert_inplace(T* A, int lda, int n, int* flag, 
 }
 
 // ---------------------------------------------------------------- blocked pivot-free LU with inverted diagonal blocks
-// One warp: factor the kb x kb block at D (ld) as P_b L U with THRESHOLD partial pivoting restricted
-// to the rows of this block (getf2-style elimination, reciprocal pivot scaling), then
-// overwrite it with [strict-lower(inv L) \ upper(inv U)] (unit diagonal of L implicit).
-// Lane i holds physical row i during elimination; rows are then redistributed so that lane i
-// holds logical (pivot-order) row i. perm[i] (i < kb) = physical row chosen as i-th pivot.
-// Returns (warp-uniform) whether the permutation is not the identity.
+// One warp: factor the NB x NB block at D (ld) as P_b L U and overwrite it with
+// [strict-lower(inv L) \ upper(inv U)] (unit diagonal of L implicit). Lane i holds physical row i
+// during elimination; perm[i] = physical row chosen as i-th pivot. Returns (warp-uniform) whether
+// the permutation is not the identity.
+//
+// Pivoting: the natural row is kept unless its pivot is below tau * (largest entry the row had when
+// the block was loaded) -- a shuffle-free scale, so the common path costs two broadcasts per pivot;
+// only then a full |max| search over the unused rows of the block runs (getf2 restricted to the
+// block). Measured (DESIGN.md "Pivoting"): eager swaps inside a block HURT fp32 trajectory parity,
+// never swapping leaves exact-zero pivots (0/0 -> NaN) on converged scenes.
+// This routine is a single-warp dependent chain (the critical path of the whole factorisation):
+// the two triangular inverses are interleaved in one loop so their chains overlap.
 template <typename T, int NB>
 __device__ __forceinline__ bool diag_block_factor_invert(T* D, int ld, int kb, int* perm) {
+  (void)kb;
   const int lane = threadIdx.x & 31;
+  const int li = lane < NB ? lane : NB - 1;      // lanes >= NB mirror the last row and never store
   T a[NB], x[NB];
+  T rmax = 0;
 #pragma unroll
-  for (int j = 0; j < NB; ++j)
-    a[j] = (lane < kb && j < kb) ? D[(size_t)lane * ld + j] : ((lane == j) ? T(1) : T(0));
-  bool done = false;      // this lane's row has been used as a pivot row
-  int myord = lane;       // lane i remembers which physical lane was the i-th pivot
+  for (int j = 0; j < NB; ++j) { a[j] = D[(size_t)li * ld + j]; rmax = fmax(rmax, fabs(a[j])); }
+  const T tau = (sizeof(T) == 4) ? T(1e-4) : T(1e-8);
+  unsigned alive = (NB == 32) ? FULL : ((1u << NB) - 1u);
+  bool done = lane >= NB;
+  int myord = lane;
   bool moved = false;
 #pragma unroll
   for (int k = 0; k < NB; ++k) {
-    // threshold partial pivoting over the not-yet-used rows of this block: keep the natural row
-    // unless its entry is below tau * (largest candidate) -- measured (DESIGN.md "Pivoting"):
-    // eager swaps inside a block HURT fp32 trajectory parity, never swapping leaves exact-zero
-    // pivots (0/0) on converged scenes; tau = 1e-4 (fp32) / 1e-8 (fp64) gives both.
-    const T mag = fabs(a[k]);
-    T best = done ? T(-1) : mag;
-    if (best != best) best = INFINITY;          // NaN: take it, everything is NaN anyway
-    int bi = lane;
+    const int nat = __ffs(alive) - 1;            // natural pivot row (uniform)
+    int pl = nat;
+    T ukk = __shfl_sync(FULL, a[k], nat);
+    const T rs = __shfl_sync(FULL, rmax, nat);
+    if (!(fabs(ukk) >= tau * rs && fabs(ukk) > T(0))) {     // rare: search the unused rows
+      T best = done ? T(-1) : fabs(a[k]);
+      if (best != best) best = INFINITY;         // NaN: take it, everything is NaN anyway
+      int bi = lane;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const T ov = __shfl_xor_sync(FULL, best, o);
-      const int oi = __shfl_xor_sync(FULL, bi, o);
-      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      for (int o = 16; o > 0; o >>= 1) {
+        const T ov = __shfl_xor_sync(FULL, best, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      pl = bi;
+      ukk = __shfl_sync(FULL, a[k], pl);
     }
-    const int nat = __ffs(__ballot_sync(FULL, !done)) - 1;     // natural pivot row
-    const T vnat = __shfl_sync(FULL, mag, nat);
-    const T tau = (sizeof(T) == 4) ? T(1e-4) : T(1e-8);
-    const int pl = (vnat > T(0) && vnat >= tau * best) ? nat : bi;   // pivot lane (uniform)
+    alive &= ~(1u << pl);
     if (lane == k) myord = pl;
     moved |= (pl != k);
-    const T ukk = __shfl_sync(FULL, a[k], pl);
-    const T r = T(1) / ukk;
     if (lane == pl) done = true;
+    const T r = T(1) / ukk;
     const bool upd = !done;
     const T l = a[k] * r;
     if (upd) a[k] = l;
 #pragma unroll
     for (int j = k + 1; j < NB; ++j) {
       const T ukj = __shfl_sync(FULL, a[j], pl);
-      if (upd) a[j] -= l * ukj;
+      if (upd) a[j] = fma(-l, ukj, a[j]);
     }
   }
-  // redistribute: lane i <- row of its pivot lane (now lane i = logical row i)
+  if (moved) {                                   // lane i <- row of its pivot lane
 #pragma unroll
-  for (int j = 0; j < NB; ++j) a[j] = __shfl_sync(FULL, a[j], myord);
-  if (lane < kb) perm[lane] = myord;
-#pragma unroll
-  for (int j = 0; j < NB; ++j) x[j] = 0;
-  // inv(L): row-oriented forward substitution, X starts as I (diagonal implicit)
-#pragma unroll
-  for (int k = 0; k < NB; ++k) {
-    const bool below = lane > k;
-    const T lik = a[k];
-#pragma unroll
-    for (int j = 0; j < k; ++j) {
-      const T xkj = __shfl_sync(FULL, x[j], k);
-      if (below) x[j] -= lik * xkj;
-    }
-    if (below) x[k] -= lik;
+    for (int j = 0; j < NB; ++j) a[j] = __shfl_sync(FULL, a[j], myord);
   }
-  // inv(U): row-oriented back substitution into the upper part of the same registers
+  if (lane < NB) perm[lane] = myord;
+  // reciprocal of the own diagonal entry of U, off the dependent chain
+  T dg = T(1);
 #pragma unroll
   for (int j = 0; j < NB; ++j)
-    if (j == lane) x[j] = T(1);
+    if (j == lane) dg = a[j];
+  const T rown = T(1) / dg;
 #pragma unroll
-  for (int k = NB - 1; k >= 0; --k) {
-    const T rk = T(1) / __shfl_sync(FULL, a[k], k);
-    const bool above = lane < k;
-    const T uik = a[k];
+  for (int j = 0; j < NB; ++j) x[j] = (j == lane) ? T(1) : T(0);
+  // inv(L) by row-oriented forward substitution (ascending k) and inv(U) by row-oriented back
+  // substitution (descending kk), interleaved; they touch disjoint halves of x in every lane.
 #pragma unroll
-    for (int j = k; j < NB; ++j) {
-      if (lane == k) x[j] *= rk;
-      const T xkj = __shfl_sync(FULL, x[j], k);
-      if (above) x[j] -= uik * xkj;
+  for (int k = 0; k < NB; ++k) {
+    {
+      const bool below = lane > k;
+      const T lik = a[k];
+#pragma unroll
+      for (int j = 0; j < k; ++j) {
+        const T xkj = __shfl_sync(FULL, x[j], k);
+        if (below) x[j] = fma(-lik, xkj, x[j]);
+      }
+      if (below) x[k] -= lik;
+    }
+    {
+      const int kk = NB - 1 - k;
+      const T rk = __shfl_sync(FULL, rown, kk);
+      const bool above = lane < kk;
+      const T uik = a[kk];
+#pragma unroll
+      for (int j = kk; j < NB; ++j) {
+        if (lane == kk) x[j] *= rk;
+        const T xkj = __shfl_sync(FULL, x[j], kk);
+        if (above) x[j] = fma(-uik, xkj, x[j]);
+      }
     }
   }
-  if (lane < kb) {
+  // the unit diagonal of inv(L) is implicit: x[lane] currently holds inv(U)[lane][lane]
+  if (lane < NB) {
 #pragma unroll
-    for (int j = 0; j < NB; ++j)
-      if (j < kb) D[(size_t)lane * ld + j] = x[j];
+    for (int j = 0; j < NB; ++j) D[(size_t)lane * ld + j] = x[j];
   }
   return moved;
 }

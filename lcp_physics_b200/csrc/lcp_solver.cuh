@@ -1,154 +1,409 @@
-// lcp_solver.cuh -- per-scene PDIPM forward / implicit-diff backward kernels.
+// lcp_solver.cuh -- per-scene PDIPM forward / implicit-diff backward kernels (v2).
 //
 // Restates (B200-native, one CTA per scene, persistent grid):
 //   pdipm.py:357-408 pre_factor_kkt, :414-454 factor_kkt, :325-354 solve_kkt,
 //   :49-179 forward, :182-186 get_step, lcp.py:22-64 LCPFunction.forward/backward.
+//
+// Residency (Plan.mode): 0 = T (padded m x m) fully in shared memory; 1 = split (lcp_lu.cuh):
+// L-shaped part in shared memory, U12 spilled to L2; 2 = T in an L2 workspace (huge problems).
+// Vectors always live in shared memory; G and Q^{-1} join them when there is room.
 #pragma once
-#include "lcp_device.cuh"
+#include "lcp_lu.cuh"
 
 namespace lcpb200 {
 
-// Launch plan, computed on the host (plan.cu) and passed by value.
 struct Plan {
   int n, m, e;
+  int mp;                     // m padded to a multiple of the LU block size
+  int m1;                     // rows held in `main` (== mp unless split)
   int nt;                     // threads per CTA
-  int grid;                   // CTAs (persistent)
-  int ldT, ldG, ldQi;         // leading dimensions of T, G copy, Qinv
-  int T_smem, G_smem, Qi_smem;
-  int off_T, off_G, off_Qi, off_vec;   // shared offsets, in elements
+  int grid;                   // resident CTAs
+  int mode;                   // 0 smem, 1 split, 2 L2
+  int ldT, ldL, ldG, ldQi;
+  int stage_ld;               // leading dimension for staging G in T's region during pre-factor (0 = no)
+  int G_smem, Qi_smem;
+  int off_T, off_L, off_G, off_Qi, off_vec;   // shared offsets, in elements
   int smem_bytes;
   long long ws_per_cta;       // workspace elements per CTA
-  long long w_Qi, w_R, w_T, w_X, w_XA, w_S11, w_V, w_W;   // workspace offsets (elements)
+  long long w_Qi, w_R, w_T, w_U12, w_X, w_XA, w_S11, w_V, w_W;
 };
 
-// Shared-memory vectors. `carve` is used with base == nullptr on the host to size the block.
+// phases for the optional cycle counters
+enum { PH_PREFACTOR = 0, PH_LOADT, PH_LU, PH_SOLVE, PH_RESID, PH_STEP, PH_COUNT };
+
 template <typename T>
 struct Vecs {
   T *x, *s, *z, *y, *d;
   T *rx, *rz, *ry;
-  T *hz, *hy, *te;            // Schur rhs / solution pieces
-  T *tn, *tn2;                // n-length temporaries
-  T *dxa, *dsa, *dza, *dya;   // affine direction
-  T *dxc, *dsc, *dzc, *dyc;   // corrector direction
+  T *hz, *hy, *te;
+  T *tn, *tn2;
+  T *dxa, *dsa, *dza, *dya;
+  T *dxc, *dsc, *dzc, *dyc;
   T *rs2;
-  T *scratch;                 // blockDim.x elements
+  T *scratch;                 // max(4 nt, mp) elements
   T *red;                     // 128 elements
-  int *perm;                  // m ints: block-local LU row interchanges
-  __host__ __device__ long long carve(T* base, int n, int m, int e, int nt) {
+  int *perm;                  // mp ints
+  __host__ __device__ long long carve(T* base, int n, int mp, int e, int nt) {
     long long o = 0;
 #define LCPB200_TAKE(ptr, cnt) do { ptr = base + o; o += ((cnt) + 3) & ~3; } while (0)
-    LCPB200_TAKE(x, n); LCPB200_TAKE(s, m); LCPB200_TAKE(z, m); LCPB200_TAKE(y, e); LCPB200_TAKE(d, m);
-    LCPB200_TAKE(rx, n); LCPB200_TAKE(rz, m); LCPB200_TAKE(ry, e);
-    LCPB200_TAKE(hz, m); LCPB200_TAKE(hy, e); LCPB200_TAKE(te, e);
+    LCPB200_TAKE(x, n); LCPB200_TAKE(s, mp); LCPB200_TAKE(z, mp); LCPB200_TAKE(y, e); LCPB200_TAKE(d, mp);
+    LCPB200_TAKE(rx, n); LCPB200_TAKE(rz, mp); LCPB200_TAKE(ry, e);
+    LCPB200_TAKE(hz, mp); LCPB200_TAKE(hy, e); LCPB200_TAKE(te, e);
     LCPB200_TAKE(tn, n); LCPB200_TAKE(tn2, n);
-    LCPB200_TAKE(dxa, n); LCPB200_TAKE(dsa, m); LCPB200_TAKE(dza, m); LCPB200_TAKE(dya, e);
-    LCPB200_TAKE(dxc, n); LCPB200_TAKE(dsc, m); LCPB200_TAKE(dzc, m); LCPB200_TAKE(dyc, e);
-    LCPB200_TAKE(rs2, m);
-    LCPB200_TAKE(scratch, (nt > n ? nt : n) > m ? (nt > n ? nt : n) : m); LCPB200_TAKE(red, 128);
-    { T* pp; LCPB200_TAKE(pp, m); perm = reinterpret_cast<int*>(pp); }
+    LCPB200_TAKE(dxa, n); LCPB200_TAKE(dsa, mp); LCPB200_TAKE(dza, mp); LCPB200_TAKE(dya, e);
+    LCPB200_TAKE(dxc, n); LCPB200_TAKE(dsc, mp); LCPB200_TAKE(dzc, mp); LCPB200_TAKE(dyc, e);
+    LCPB200_TAKE(rs2, mp);
+    LCPB200_TAKE(scratch, 4 * nt > mp ? 4 * nt : mp); LCPB200_TAKE(red, 128);
+    { T* pp; LCPB200_TAKE(pp, mp); perm = reinterpret_cast<int*>(pp); }
 #undef LCPB200_TAKE
     return o;
   }
 };
 
-template <typename T>
+template <typename T, int MODE>
 struct SceneCtx {
-  int n, m, e;
+  int n, m, e, mp, nt, off_vec;
   const T *Q, *G, *A, *F;     // this scene's inputs (G may point at the shared copy)
   int ldG;
   T *Qi; int ldQi;
-  T *Tm; int ldT;
+  TView<T, MODE> tv;
   T *R, *X, *XA, *S11, *Vm, *W;
-  int* lu_flag;               // shared int used by lu_blocked
-  Vecs<T> v;
+  bool Rsaved;                // R points at a matrix saved by the forward pass (read-only)
+  int stage_ld;               // > 0: G may be staged in T's shared region with this leading dimension
+  const T* Gsrc;              // this scene's G in global memory
+  int* lu_flag;
+  long long* prof;            // nullptr or PH_COUNT counters (thread 0 only)
+  long long t_last;
+  // shared-memory vectors, rebuilt from the namespace-scope shared array so the pointers are
+  // provably shared inside every (non-inlined) device function
+  __device__ __forceinline__ Vecs<T> vecs() const {
+    Vecs<T> v;
+    v.carve(smem_base<T>() + off_vec, n, mp, e, nt);
+    return v;
+  }
 };
 
-// ------------------------------------------------------------------ pre_factor_kkt (pdipm.py:357-408)
-// Returns false (uniformly) when Q is singular.
-template <typename T>
-__device__ bool prefactor(SceneCtx<T>& c, int* flag) {
-  const int n = c.n, m = c.m, e = c.e, tid = threadIdx.x, NT = blockDim.x;
-  if (tid == 0) *flag = 0;
-  for (int t = tid; t < n * n; t += NT) { int i = t / n, j = t - i * n; c.Qi[(size_t)i * c.ldQi + j] = c.Q[t]; }
+template <typename C>
+__device__ __forceinline__ void prof_start(C& c) { if (c.prof && threadIdx.x == 0) c.t_last = clock64(); }
+template <typename C>
+__device__ __forceinline__ void prof_lap(C& c, int ph) {
+  if (c.prof && threadIdx.x == 0) { const long long t = clock64(); c.prof[ph] += t - c.t_last; c.t_last = t; }
+}
+
+// ------------------------------------------------------------------ vector GEMVs
+// out[r] = epi(r, sum_j A[r*lda+j] x[j]): one warp per row, RB rows (and all their vectors) in
+// flight per warp so that an L2-resident matrix is streamed with deep memory-level parallelism.
+template <typename T, typename Epi>
+__device__ __forceinline__ void gemv_rows_v(const T* __restrict__ A, int lda, int M, int N, const T* x, Epi epi) {
+  using V = typename VecOf<T>::type;
+  constexpr int VC = VecOf<T>::VC;
+  constexpr int RB = 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const bool vec_ok = (N % VC == 0) && (lda % VC == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  if (vec_ok) {
+    for (int r0 = warp * RB; r0 < M; r0 += nw * RB) {
+      T acc[RB];
+#pragma unroll
+      for (int q = 0; q < RB; ++q) acc[q] = 0;
+      for (int j = lane * VC; j < N; j += 32 * VC) {
+        V av[RB];
+#pragma unroll
+        for (int q = 0; q < RB; ++q) av[q] = *reinterpret_cast<const V*>(A + (size_t)min(r0 + q, M - 1) * lda + j);
+        T xv[VC];
+        vec_get<T>(*reinterpret_cast<const V*>(x + j), xv);
+#pragma unroll
+        for (int q = 0; q < RB; ++q) {
+          T a_[VC];
+          vec_get<T>(av[q], a_);
+#pragma unroll
+          for (int t = 0; t < VC; ++t) acc[q] = fma(a_[t], xv[t], acc[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < RB; ++q) acc[q] = warp_reduce(acc[q], OpSum());
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < RB; ++q)
+          if (r0 + q < M) epi(r0 + q, acc[q]);
+      }
+    }
+    __syncthreads();
+  } else {
+    gemv_rows(A, lda, M, N, x, epi);
+  }
+}
+
+// out[j] = epi(j, sum_i A[i*lda+j] w[i]): a thread owns one column vector and a slice of the rows;
+// slices are combined through `scratch` (>= 4*blockDim.x elements).
+template <typename T, typename Epi>
+__device__ __forceinline__ void gemv_cols_v(const T* __restrict__ A, int lda, int M, int N, const T* w, T* scratch,
+                                            Epi epi) {
+  using V = typename VecOf<T>::type;
+  constexpr int VC = VecOf<T>::VC;
+  const int NT = blockDim.x;
+  const int njv = N / VC;
+  const bool vec_ok = (N % VC == 0) && (lda % VC == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && njv <= NT;
+  if (!vec_ok) { gemv_cols(A, lda, M, N, w, scratch, epi); return; }
+  const int njp = (njv + 31) & ~31;
+  const int parts = NT / njp;
+  const int part = threadIdx.x / njp, jv = threadIdx.x - part * njp;
+  T acc[VC];
+#pragma unroll
+  for (int t = 0; t < VC; ++t) acc[t] = 0;
+  if (part < parts && jv < njv) {
+    const T* col = A + jv * VC;
+#pragma unroll 8
+    for (int i = part; i < M; i += parts) {
+      T av[VC];
+      vec_get<T>(*reinterpret_cast<const V*>(col + (size_t)i * lda), av);
+      const T wi = w[i];
+#pragma unroll
+      for (int t = 0; t < VC; ++t) acc[t] = fma(av[t], wi, acc[t]);
+    }
+    *reinterpret_cast<V*>(scratch + ((size_t)part * njv + jv) * VC) = vec_make(acc);
+  }
   __syncthreads();
-  invert_inplace(c.Qi, c.ldQi, n, flag, c.v.scratch);          // :362  Q^{-1} instead of LU(Q)
+  for (int j = threadIdx.x; j < N; j += NT) {
+    T t = 0;
+    for (int q = 0; q < parts; ++q) t += scratch[(size_t)q * N + j];
+    epi(j, t);
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------ R = G diag(qi) G^T + F
+// Fast path of pdipm.py:378 for a diagonal Q (every mass matrix world.py:57-61 builds). Gs: a
+// row-major copy of G (ld = ldg == 4 mod 32 words when staged in shared memory). Thread tile 8x8:
+// rows rb + g + 4r, columns cb + cg + 8c -- both operand loads are vectors along k from
+// consecutive rows, conflict-free. R and F are the L2/HBM arrays [m,m].
+template <typename T>
+__device__ __forceinline__ void gram_diag(const T* __restrict__ Gs, int ldg, const T* qi, const T* __restrict__ F,
+                                          T* __restrict__ R, int m, int n) {
+  using V = typename VecOf<T>::type;
+  constexpr int VC = VecOf<T>::VC;
+  constexpr int TR = 8, TC = 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int g = lane >> 3, cg = lane & 7;
+  const int ntr = (m + 31) / 32, ntc = (m + 63) / 64;
+  for (int wt = warp; wt < ntr * ntc; wt += nw) {
+    const int tr_ = wt / ntc, tc_ = wt - tr_ * ntc;
+    const int rb = tr_ * 32 + g, cb = tc_ * 64 + cg;
+    const T* ap[TR];
+    const T* bp[TC];
+#pragma unroll
+    for (int r = 0; r < TR; ++r) ap[r] = Gs + (size_t)min(rb + 4 * r, m - 1) * ldg;
+#pragma unroll
+    for (int c = 0; c < TC; ++c) bp[c] = Gs + (size_t)min(cb + 8 * c, m - 1) * ldg;
+    T acc[TR][TC];
+#pragma unroll
+    for (int r = 0; r < TR; ++r)
+#pragma unroll
+      for (int c = 0; c < TC; ++c) acc[r][c] = 0;
+    for (int kc = 0; kc < n; kc += VC) {
+      T a[TR][VC], qv[VC];
+      vec_get<T>(*reinterpret_cast<const V*>(qi + kc), qv);
+#pragma unroll
+      for (int r = 0; r < TR; ++r) {
+        vec_get<T>(*reinterpret_cast<const V*>(ap[r] + kc), a[r]);
+#pragma unroll
+        for (int t = 0; t < VC; ++t) a[r][t] *= qv[t];
+      }
+#pragma unroll
+      for (int c = 0; c < TC; ++c) {
+        T b[VC];
+        vec_get<T>(*reinterpret_cast<const V*>(bp[c] + kc), b);
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+#pragma unroll
+          for (int t = 0; t < VC; ++t) acc[r][c] = fma(a[r][t], b[t], acc[r][c]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < TR; ++r) {
+      const int i = rb + 4 * r;
+      if (i >= m) continue;
+#pragma unroll
+      for (int c = 0; c < TC; ++c) {
+        const int j = cb + 8 * c;
+        if (j < m) R[(size_t)i * m + j] = F[(size_t)i * m + j] + acc[r][c];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------ pre_factor_kkt (pdipm.py:357-408)
+template <typename T, int MODE>
+__device__ __noinline__ bool prefactor(SceneCtx<T, MODE>& c, int* flag) {
+  const int n = c.n, m = c.m, e = c.e, tid = threadIdx.x, NT = blockDim.x;
+  Vecs<T> v = c.vecs();
+  if (tid == 0) *flag = 0;
+  // Q^{-1} (:362 factors Q; we keep the inverse so later Q-solves are GEMVs). Diagonal Q -- every
+  // mass matrix the engine builds (world.py:57-61) -- is inverted directly.
+  int offdiag = 0;
+  for (int t = tid; t < n * n; t += NT) { const int i = t / n, j = t - i * n; if (i != j && c.Q[t] != T(0)) offdiag = 1; }
+  offdiag = __syncthreads_or(offdiag);
+  if (!offdiag) {
+    for (int t = tid; t < n * n; t += NT) {
+      const int i = t / n, j = t - i * n;
+      T val = 0;
+      if (i == j) { const T q = c.Q[t]; if (!(q != T(0) && isfinite((double)q))) *flag = 1; val = T(1) / q; }
+      c.Qi[(size_t)i * c.ldQi + j] = val;
+    }
+    __syncthreads();
+  } else {
+    for (int t = tid; t < n * n; t += NT) { const int i = t / n, j = t - i * n; c.Qi[(size_t)i * c.ldQi + j] = c.Q[t]; }
+    __syncthreads();
+    invert_inplace(c.Qi, c.ldQi, n, flag, v.scratch);
+  }
   const bool singular = (*flag != 0);
   __syncthreads();
   if (singular) return false;
-  // X = Q^{-1} G^T ; R = G X + F                                 :378-379
-  gemm_tiled<T, true>(c.X, m, c.Qi, c.ldQi, c.G, c.ldG, n, m, n, T(1), T(0));
-  for (int t = tid; t < m * m; t += NT) c.R[t] = c.F[t];
-  __syncthreads();
-  gemm_tiled<T, false>(c.R, m, c.G, c.ldG, c.X, m, m, m, n, T(1), T(1));
+  constexpr int VC_ = VecOf<T>::VC;
+  if (c.Rsaved) {
+    // R was saved by the forward pass (backward only): nothing to form
+  } else if (!offdiag && n % VC_ == 0) {
+    // R = G diag(1/q) G^T + F with G staged in the (still unused) shared-memory region of T
+    T* qd = v.scratch;                                           // n <= scratch
+    for (int i = tid; i < n; i += NT) qd[i] = c.Qi[(size_t)i * c.ldQi + i];
+    const int ldgs = c.stage_ld;
+    if (MODE != 2 && ldgs > 0) {
+      T* Gs = c.tv.main();
+      const int nv = n / VC_;
+      using V_ = typename VecOf<T>::type;
+      const bool gal = (reinterpret_cast<uintptr_t>(c.Gsrc) & 15) == 0;
+      if (gal) {
+#pragma unroll 4
+        for (int t = tid; t < m * nv; t += NT) {
+          const int i = t / nv, j = (t - i * nv) * VC_;
+          *reinterpret_cast<V_*>(Gs + (size_t)i * ldgs + j) = *reinterpret_cast<const V_*>(c.Gsrc + (size_t)i * n + j);
+        }
+      } else {
+        for (int t = tid; t < m * n; t += NT) { const int i = t / n, j = t - i * n; Gs[(size_t)i * ldgs + j] = c.Gsrc[t]; }
+      }
+      __syncthreads();
+      gram_diag<T>(Gs, ldgs, qd, c.F, c.R, m, n);
+    } else {
+      __syncthreads();
+      gram_diag<T>(c.G, c.ldG, qd, c.F, c.R, m, n);
+    }
+  } else {
+    // X = Q^{-1} G^T ; R = G X + F                                 :378-379
+    gemm_tiled<T, true>(c.X, m, c.Qi, c.ldQi, c.G, c.ldG, n, m, n, T(1), T(0));
+    for (int t = tid; t < m * m; t += NT) c.R[t] = c.F[t];
+    __syncthreads();
+    gemm_tiled<T, false>(c.R, m, c.G, c.ldG, c.X, m, m, m, n, T(1), T(1));
+  }
   if (e > 0) {
-    // XA = Q^{-1} A^T (:383), S11 = A XA (:384), V = G XA (:385)
-    gemm_tiled<T, true>(c.XA, e, c.Qi, c.ldQi, c.A, n, n, e, n, T(1), T(0));
-    gemm_tiled<T, false>(c.S11, e, c.A, n, c.XA, e, e, e, n, T(1), T(0));
-    gemm_tiled<T, false>(c.Vm, e, c.G, c.ldG, c.XA, e, m, e, n, T(1), T(0));
-    invert_inplace(c.S11, e, e, flag, c.v.scratch);            // :387  (A Q^{-1} A^T)^{-1}
-    // W = S11^{-1} V^T (:395, the reference reuses (G Q^{-1} A^T)^T here) ; R -= V W (:403)
-    gemm_tiled<T, true>(c.W, m, c.S11, e, c.Vm, e, e, m, e, T(1), T(0));
-    gemm_tiled<T, false>(c.R, m, c.Vm, e, c.W, m, m, m, e, T(-1), T(1));
+    gemm_tiled<T, true>(c.XA, e, c.Qi, c.ldQi, c.A, n, n, e, n, T(1), T(0));          // :383
+    gemm_tiled<T, false>(c.S11, e, c.A, n, c.XA, e, e, e, n, T(1), T(0));              // :384
+    gemm_tiled<T, false>(c.Vm, e, c.G, c.ldG, c.XA, e, m, e, n, T(1), T(0));           // :385
+    invert_inplace(c.S11, e, e, flag, v.scratch);                                    // :387
+    gemm_tiled<T, true>(c.W, m, c.S11, e, c.Vm, e, e, m, e, T(1), T(0));               // :395
+    if (!c.Rsaved) gemm_tiled<T, false>(c.R, m, c.Vm, e, c.W, m, m, m, e, T(-1), T(1));   // :403
   }
   return true;
 }
 
 // ------------------------------------------------------------------ factor_kkt (pdipm.py:414-454)
-template <typename T>
-__device__ void factor_kkt(SceneCtx<T>& c, const T* d) {
-  const int m = c.m;
-  for (int t = threadIdx.x; t < m * m; t += blockDim.x) {
-    const int i = t / m, j = t - i * m;
-    T val = c.R[t];
-    if (i == j) val += T(1) / d[i];                              // :427-429
-    c.Tm[(size_t)i * c.ldT + j] = val;
+// T = R + diag(1/d) (:427-429), padded with an identity block, loaded into the view, then LU (:431).
+template <typename T, int MODE>
+__device__ __noinline__ void factor_kkt(SceneCtx<T, MODE>& c) {
+  using V = typename VecOf<T>::type;
+  constexpr int VC = VecOf<T>::VC;
+  const int m = c.m, mp = c.mp, m1 = c.tv.m1, tid = threadIdx.x, NT = blockDim.x;
+  Vecs<T> v = c.vecs();
+  const T* d = v.d;
+  T* dinv = v.scratch;                                            // mp elements
+  T* const tmain = c.tv.main();
+  T* const tlow = (MODE == 1) ? c.tv.low() : tmain;
+  for (int i = tid; i < mp; i += NT) dinv[i] = i < m ? T(1) / d[i] : T(1);
+  __syncthreads();
+  const bool vec_ok = (m % VC == 0) && ((reinterpret_cast<uintptr_t>(c.R) & 15) == 0);
+  if (vec_ok) {
+    const int mv = mp / VC;
+    // main rows [0,m1) x all columns
+#pragma unroll 4
+    for (int t = tid; t < m1 * mv; t += NT) {
+      const int i = t / mv, j = (t - i * mv) * VC;
+      T val[VC];
+      if (i < m && j < m) vec_get<T>(*reinterpret_cast<const V*>(c.R + (size_t)i * m + j), val);
+      else { for (int q = 0; q < VC; ++q) val[q] = 0; }
+      if (i >= j && i < j + VC) val[i - j] += dinv[i];
+      *reinterpret_cast<V*>(tmain + (size_t)i * c.tv.ld + j) = vec_make(val);
+    }
+    // low rows [m1,mp) x columns [0,m1)
+    const int m1v = m1 / VC;
+#pragma unroll 4
+    for (int t = tid; t < (mp - m1) * m1v; t += NT) {
+      const int i = m1 + t / m1v, j = (t % m1v) * VC;
+      T val[VC];
+      if (i < m && j < m) vec_get<T>(*reinterpret_cast<const V*>(c.R + (size_t)i * m + j), val);
+      else { for (int q = 0; q < VC; ++q) val[q] = 0; }
+      *reinterpret_cast<V*>(tlow + (size_t)(i - m1) * c.tv.ldl + j) = vec_make(val);
+    }
+  } else {
+    for (int t = tid; t < m1 * mp; t += NT) {
+      const int i = t / mp, j = t - i * mp;
+      T val = (i < m && j < m) ? c.R[(size_t)i * m + j] : T(0);
+      if (i == j) val += dinv[i];
+      tmain[(size_t)i * c.tv.ld + j] = val;
+    }
+    for (int t = tid; t < (mp - m1) * m1; t += NT) {
+      const int i = m1 + t / m1, j = t % m1;
+      tlow[(size_t)(i - m1) * c.tv.ldl + j] = (i < m && j < m) ? c.R[(size_t)i * m + j] : T(0);
+    }
   }
   __syncthreads();
-  lu_blocked(c.Tm, c.ldT, m, c.v.perm, c.lu_flag);                // :431 (block-local pivoting)
+  prof_lap(c, PH_LOADT);
+  lu_factor_view<T, MODE>(c.tv, c.R + (size_t)m1 * m + m1, m, dinv, m, v.perm, c.lu_flag, v.red);
+  prof_lap(c, PH_LU);
 }
 
 // ------------------------------------------------------------------ solve_kkt (pdipm.py:325-354)
-// rx / rz / ry may be nullptr (== zero vector). Outputs may not alias the inputs.
-template <typename T>
-__device__ void solve_kkt(SceneCtx<T>& c, const T* d, const T* rx, const T* rs, const T* rz, const T* ry,
-                          T* dx, T* ds, T* dz, T* dy) {
+// Vectors are passed as element offsets into the shared array (-1 == zero vector) so that the
+// pointers formed here are provably shared.
+template <typename T, int MODE>
+__device__ __noinline__ void solve_kkt(SceneCtx<T, MODE>& c, int o_rx, int o_rs, int o_rz, int o_ry,
+                                       int o_dx, int o_ds, int o_dz, int o_dy) {
   const int n = c.n, m = c.m, e = c.e, tid = threadIdx.x, NT = blockDim.x;
-  Vecs<T>& v = c.v;
+  Vecs<T> v = c.vecs();
+  T* const sb = smem_base<T>();
+  const T* d = v.d;
+  const T* rx = o_rx >= 0 ? sb + o_rx : nullptr;
+  const T* rs = sb + o_rs;
+  const T* rz = o_rz >= 0 ? sb + o_rz : nullptr;
+  const T* ry = o_ry >= 0 ? sb + o_ry : nullptr;
+  T* dx = sb + o_dx; T* ds = sb + o_ds; T* dz = sb + o_dz; T* dy = sb + o_dy;
   T* t = v.tn;                                                   // Q^{-1} rx      :333
   if (rx) {
-    gemv_rows(c.Qi, c.ldQi, n, n, rx, [&](int i, T a) { t[i] = a; });
-    // hz = G t + rs/d - rz ; hy = A t - ry                       :337-340
-    gemv_rows(c.G, c.ldG, m, n, t, [&](int i, T a) { v.hz[i] = a + rs[i] / d[i] - (rz ? rz[i] : T(0)); });
-    if (e > 0) gemv_rows(c.A, n, e, n, t, [&](int i, T a) { v.hy[i] = a - (ry ? ry[i] : T(0)); });
+    gemv_rows_v(c.Qi, c.ldQi, n, n, rx, [&](int i, T a) { t[i] = a; });
+    gemv_rows_v(c.G, c.ldG, m, n, t, [&](int i, T a) { v.hz[i] = a + rs[i] / d[i] - (rz ? rz[i] : T(0)); });   // :337-340
+    if (e > 0) gemv_rows_v(c.A, n, e, n, t, [&](int i, T a) { v.hy[i] = a - (ry ? ry[i] : T(0)); });
   } else {
     for (int i = tid; i < m; i += NT) v.hz[i] = rs[i] / d[i] - (rz ? rz[i] : T(0));
     for (int i = tid; i < e; i += NT) v.hy[i] = -(ry ? ry[i] : T(0));
     __syncthreads();
   }
-  // w = -S^{-1} h by block elimination of the e x e block          :342
-  if (e > 0) {
-    gemv_rows(c.S11, e, e, e, v.hy, [&](int i, T a) { v.te[i] = a; });
-    gemv_rows(c.Vm, e, m, e, v.te, [&](int i, T a) { v.hz[i] -= a; });
+  if (e > 0) {                                                   // block elimination of the e x e block  :342
+    gemv_rows_v(c.S11, e, e, e, v.hy, [&](int i, T a) { v.te[i] = a; });
+    gemv_rows_v(c.Vm, e, m, e, v.te, [&](int i, T a) { v.hz[i] -= a; });
   }
-  lu_solve_vec(c.Tm, c.ldT, m, v.perm, v.hz, v.scratch);         // hz <- T^{-1}(..) = -w_z
-  if (e > 0) {
-    gemv_rows(c.W, m, e, m, v.hz, [&](int i, T a) { dy[i] = -(v.te[i] - a); });   // w_y
-  }
+  lu_solve_view<T, MODE>(c.tv, v.perm, v.hz, v.scratch);               // hz <- T^{-1}(..) = -w_z   (hz[m..mp) stays 0)
+  if (e > 0) gemv_rows_v(c.W, m, e, m, v.hz, [&](int i, T a) { dy[i] = -(v.te[i] - a); });
   for (int i = tid; i < m; i += NT) {
     const T wz = -v.hz[i];
     dz[i] = wz;                                                  // :351
     ds[i] = (-rs[i] - wz) / d[i];                                // :347,350
   }
   __syncthreads();
-  // g1 = -rx - G^T w_z - A^T w_y ; dx = Q^{-1} g1                 :344-349
-  T* g1 = v.tn2;
-  gemv_cols(c.G, c.ldG, m, n, dz, v.scratch, [&](int j, T a) { g1[j] = -(rx ? rx[j] : T(0)) - a; });
-  if (e > 0) gemv_cols(c.A, n, e, n, dy, v.scratch, [&](int j, T a) { g1[j] -= a; });
-  gemv_rows(c.Qi, c.ldQi, n, n, g1, [&](int i, T a) { dx[i] = a; });
+  T* g1 = v.tn2;                                                 // :344-349
+  gemv_cols_v(c.G, c.ldG, m, n, dz, v.scratch, [&](int j, T a) { g1[j] = -(rx ? rx[j] : T(0)) - a; });
+  if (e > 0) gemv_cols_v(c.A, n, e, n, dy, v.scratch, [&](int j, T a) { g1[j] -= a; });
+  gemv_rows_v(c.Qi, c.ldQi, n, n, g1, [&](int i, T a) { dx[i] = a; });
 }
 
 // ------------------------------------------------------------------ get_step (pdipm.py:182-186), per scene
-// Returns (step(z,dz), step(s,ds)) with torch's NaN semantics.
 template <typename T>
 __device__ void get_steps(const T* z, const T* dz, const T* s, const T* ds, int m, T* red, T& step_z, T& step_s) {
   const T NEG_INF = -INFINITY, POS_INF = INFINITY;
@@ -182,22 +437,43 @@ struct FwdArgs {
   T eps;
   int not_improved_lim, max_iter;
   T* ws;
+  T* Rsave;                   // nullptr or [B,m,m]: R of every scene, for the backward pass
+  long long* prof;            // nullptr or [grid][PH_COUNT]
 };
 
-template <typename T>
-__device__ void setup_ctx(SceneCtx<T>& c, const Plan& P, T* sm, T* ws) {
-  c.n = P.n; c.m = P.m; c.e = P.e;
+template <typename T, int MODE>
+__device__ void setup_ctx(SceneCtx<T, MODE>& c, const Plan& P, T* sm, T* ws, int* lu_flag, long long* prof) {
+  c.n = P.n; c.m = P.m; c.e = P.e; c.mp = P.mp; c.nt = P.nt; c.off_vec = P.off_vec;
   c.Qi = P.Qi_smem ? sm + P.off_Qi : ws + P.w_Qi; c.ldQi = P.ldQi;
-  c.Tm = P.T_smem ? sm + P.off_T : ws + P.w_T;    c.ldT = P.ldT;
+  c.tv.mp = P.mp; c.tv.m1 = P.m1;
+  c.tv.main_off = P.off_T; c.tv.low_off = P.off_L; c.tv.main_g = ws + P.w_T;
+  c.tv.ld = P.ldT; c.tv.ldl = P.ldL;
+  c.tv.u12 = ws + P.w_U12;
   c.R = ws + P.w_R; c.X = ws + P.w_X; c.XA = ws + P.w_XA; c.S11 = ws + P.w_S11;
   c.Vm = ws + P.w_V; c.W = ws + P.w_W;
-  c.v.carve(sm + P.off_vec, P.n, P.m, P.e, P.nt);
+  c.Rsaved = false; c.stage_ld = P.stage_ld; c.Gsrc = nullptr;
+  c.lu_flag = lu_flag;
+  c.prof = prof ? prof + (size_t)blockIdx.x * PH_COUNT : nullptr;
+  Vecs<T> v = c.vecs();
+  // padded tails: never written again
+  for (int i = P.m + threadIdx.x; i < P.mp; i += blockDim.x) {
+    v.hz[i] = 0; v.s[i] = 1; v.z[i] = 1; v.d[i] = 1; v.rz[i] = 0; v.rs2[i] = 0;
+    v.dsa[i] = 0; v.dza[i] = 0; v.dsc[i] = 0; v.dzc[i] = 0;
+  }
+  __syncthreads();
 }
 
-template <typename T>
-__device__ void bind_scene(SceneCtx<T>& c, const Plan& P, T* sm, const T* Q, const T* G, const T* A, const T* F) {
+template <typename T, int MODE>
+__device__ void bind_scene(SceneCtx<T, MODE>& c, const Plan& P, T* sm, const T* Q, const T* G, const T* A, const T* F) {
   const int n = P.n, m = P.m;
-  c.Q = Q; c.A = A; c.F = F;
+  c.Q = Q; c.A = A; c.F = F; c.Gsrc = G;
+  {   // padded tails: a NaN produced by the previous scene must not leak into this one
+    Vecs<T> v = c.vecs();
+    for (int i = P.m + threadIdx.x; i < P.mp; i += blockDim.x) {
+      v.hz[i] = 0; v.s[i] = 1; v.z[i] = 1; v.d[i] = 1; v.rz[i] = 0; v.rs2[i] = 0;
+      v.dsa[i] = 0; v.dza[i] = 0; v.dsc[i] = 0; v.dzc[i] = 0;
+    }
+  }
   if (P.G_smem) {
     T* Gs = sm + P.off_G;
     for (int t = threadIdx.x; t < m * n; t += blockDim.x) { int i = t / n, j = t - i * n; Gs[(size_t)i * P.ldG + j] = G[t]; }
@@ -209,18 +485,18 @@ __device__ void bind_scene(SceneCtx<T>& c, const Plan& P, T* sm, const T* Q, con
 }
 
 // ------------------------------------------------------------------ forward (pdipm.py:49-179)
-template <typename T>
-__global__ void __launch_bounds__(512) lcp_forward_kernel(const FwdArgs<T> a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* sm = reinterpret_cast<T*>(smem_raw);
+template <typename T, int MODE>
+__global__ void __launch_bounds__(512, 1) lcp_forward_kernel(const FwdArgs<T> a) {
+  T* sm = smem_base<T>();
   __shared__ int flag;
   __shared__ int lu_flag_s;
   const Plan& P = a.P;
   const int n = P.n, m = P.m, e = P.e, tid = threadIdx.x, NT = blockDim.x;
-  SceneCtx<T> c;
-  setup_ctx(c, P, sm, a.ws + (size_t)blockIdx.x * P.ws_per_cta);
-  c.lu_flag = &lu_flag_s;
-  Vecs<T>& v = c.v;
+  SceneCtx<T, MODE> c;
+  setup_ctx<T, MODE>(c, P, sm, a.ws + (size_t)blockIdx.x * P.ws_per_cta, &lu_flag_s, a.prof);
+  Vecs<T> v = c.vecs();
+  T* const sb = sm;
+  auto off = [&](const T* p_) { return (int)(p_ - sb); };
   const T NANV = nan("");
 
   for (int sc = blockIdx.x; sc < a.B; sc += gridDim.x) {
@@ -231,8 +507,10 @@ __global__ void __launch_bounds__(512) lcp_forward_kernel(const FwdArgs<T> a) {
     T* o_z = a.lam + (size_t)sc * m;
     T* o_s = a.slack + (size_t)sc * m;
     T* o_y = e > 0 ? a.nu + (size_t)sc * e : nullptr;
+    prof_start(c);
     bind_scene(c, P, sm, a.Q + (size_t)sc * n * n, a.G + (size_t)sc * m * n,
                e > 0 ? a.A + (size_t)sc * e * n : nullptr, a.F + (size_t)sc * m * m);
+    if (a.Rsave) c.R = a.Rsave + (size_t)sc * m * m;      // form R directly in the saved buffer
 
     if (!prefactor(c, &flag)) {
       for (int i = tid; i < n; i += NT) o_x[i] = NANV;
@@ -242,14 +520,15 @@ __global__ void __launch_bounds__(512) lcp_forward_kernel(const FwdArgs<T> a) {
       __syncthreads();
       continue;
     }
+    prof_lap(c, PH_PREFACTOR);
 
     // ---- initial point: d = 1, rhs (p, 0, -h, -b)                 :58-63
     for (int i = tid; i < m; i += NT) { v.d[i] = T(1); v.rs2[i] = T(0); v.rz[i] = -h[i]; }
     for (int i = tid; i < n; i += NT) v.rx[i] = p[i];
     for (int i = tid; i < e; i += NT) v.ry[i] = -b[i];
     __syncthreads();
-    factor_kkt(c, v.d);
-    solve_kkt(c, v.d, v.rx, v.rs2, v.rz, e > 0 ? v.ry : nullptr, v.x, v.s, v.z, v.y);
+    factor_kkt(c);
+    solve_kkt(c, off(v.rx), off(v.rs2), off(v.rz), e > 0 ? off(v.ry) : -1, off(v.x), off(v.s), off(v.z), off(v.y));
     {   // shift s and z to >= 1 where the row minimum is <= 0       :65-75
       T mn[2] = {INFINITY, INFINITY};
       for (int i = tid; i < m; i += NT) { mn[0] = nan_min(mn[0], v.s[i]); mn[1] = nan_min(mn[1], v.z[i]); }
@@ -260,20 +539,19 @@ __global__ void __launch_bounds__(512) lcp_forward_kernel(const FwdArgs<T> a) {
       }
       __syncthreads();
     }
+    prof_lap(c, PH_SOLVE);
 
     T best = NANV;
     bool have_best = false;
     int not_improved = 0, status = 0, it = 0;
     for (it = 0; it < a.max_iter; ++it) {
       // ---- residuals                                              :82-96
-      // rx = A^T y + G^T z + Q x + p
-      gemv_cols(c.G, c.ldG, m, n, v.z, v.scratch, [&](int j, T acc) { v.rx[j] = acc; });
-      if (e > 0) gemv_cols(c.A, n, e, n, v.y, v.scratch, [&](int j, T acc) { v.rx[j] = acc + v.rx[j]; });
-      gemv_rows(c.Q, n, n, n, v.x, [&](int i, T acc) { v.rx[i] = v.rx[i] + acc + p[i]; });
-      // rz = G x + s - h - F z
-      gemv_rows(c.G, c.ldG, m, n, v.x, [&](int i, T acc) { v.rz[i] = acc + v.s[i] - h[i]; });
-      gemv_rows(c.F, m, m, m, v.z, [&](int i, T acc) { v.rz[i] -= acc; });
-      if (e > 0) gemv_rows(c.A, n, e, n, v.x, [&](int i, T acc) { v.ry[i] = acc - b[i]; });
+      gemv_cols_v(c.G, c.ldG, m, n, v.z, v.scratch, [&](int j, T acc) { v.rx[j] = acc; });
+      if (e > 0) gemv_cols_v(c.A, n, e, n, v.y, v.scratch, [&](int j, T acc) { v.rx[j] = acc + v.rx[j]; });
+      gemv_rows_v(c.Q, n, n, n, v.x, [&](int i, T acc) { v.rx[i] = v.rx[i] + acc + p[i]; });
+      gemv_rows_v(c.G, c.ldG, m, n, v.x, [&](int i, T acc) { v.rz[i] = acc + v.s[i] - h[i]; });
+      gemv_rows_v(c.F, m, m, m, v.z, [&](int i, T acc) { v.rz[i] -= acc; });
+      if (e > 0) gemv_rows_v(c.A, n, e, n, v.x, [&](int i, T acc) { v.ry[i] = acc - b[i]; });
       T q[4] = {0, 0, 0, 0};                                      // s.z, |rz|^2, |ry|^2, |rx|^2
       for (int i = tid; i < m; i += NT) { q[0] += v.s[i] * v.z[i]; q[1] += v.rz[i] * v.rz[i]; }
       for (int i = tid; i < e; i += NT) q[2] += v.ry[i] * v.ry[i];
@@ -283,10 +561,10 @@ __global__ void __launch_bounds__(512) lcp_forward_kernel(const FwdArgs<T> a) {
       const T mu = fabs(sz / T(m));                               // :91
       const T resid = (e > 0 ? sqrt(q[2]) : T(0)) + sqrt(q[1]) + sqrt(q[3]) + T(m) * mu;   // :92-96
 
-      // ---- d = z/s, factor                                        :98-100
-      for (int i = tid; i < m; i += NT) v.d[i] = v.z[i] / v.s[i];
+      for (int i = tid; i < m; i += NT) v.d[i] = v.z[i] / v.s[i];     // :98
       __syncthreads();
-      factor_kkt(c, v.d);
+      prof_lap(c, PH_RESID);
+      factor_kkt(c);                                         // :100
 
       // ---- best iterate / termination (per scene)                 :107-136
       bool improved;
@@ -303,7 +581,8 @@ __global__ void __launch_bounds__(512) lcp_forward_kernel(const FwdArgs<T> a) {
       if (mu > T(1e100)) { status = 3; ++it; break; }
 
       // ---- affine direction                                       :138-139   (rs = z)
-      solve_kkt(c, v.d, v.rx, v.z, v.rz, e > 0 ? v.ry : nullptr, v.dxa, v.dsa, v.dza, v.dya);
+      solve_kkt(c, off(v.rx), off(v.z), off(v.rz), e > 0 ? off(v.ry) : -1, off(v.dxa), off(v.dsa), off(v.dza), off(v.dya));
+      prof_lap(c, PH_SOLVE);
       T stz, sts;
       get_steps(v.z, v.dza, v.s, v.dsa, m, v.red, stz, sts);
       const T alpha_aff = nan_min(nan_min(stz, sts), T(1));       // :142-144
@@ -312,11 +591,12 @@ __global__ void __launch_bounds__(512) lcp_forward_kernel(const FwdArgs<T> a) {
       block_reduce<T, 1>(t3, OpSum(), T(0), v.red);
       const T ratio = t3[0] / sz;                                 // :146-150
       const T sig = ratio * ratio * ratio;
-      // ---- corrector                                              :152-158
-      const T musig = -mu * sig;
+      const T musig = -mu * sig;                                  // :152-158
       for (int i = tid; i < m; i += NT) v.rs2[i] = (musig + v.dsa[i] * v.dza[i]) / v.s[i];
       __syncthreads();
-      solve_kkt(c, v.d, (const T*)nullptr, v.rs2, (const T*)nullptr, (const T*)nullptr, v.dxc, v.dsc, v.dzc, v.dyc);
+      prof_lap(c, PH_STEP);
+      solve_kkt(c, -1, off(v.rs2), -1, -1, off(v.dxc), off(v.dsc), off(v.dzc), off(v.dyc));
+      prof_lap(c, PH_SOLVE);
       for (int i = tid; i < n; i += NT) v.dxa[i] += v.dxc[i];    // :160-163
       for (int i = tid; i < m; i += NT) { v.dsa[i] += v.dsc[i]; v.dza[i] += v.dzc[i]; }
       for (int i = tid; i < e; i += NT) v.dya[i] += v.dyc[i];
@@ -327,6 +607,7 @@ __global__ void __launch_bounds__(512) lcp_forward_kernel(const FwdArgs<T> a) {
       for (int i = tid; i < m; i += NT) { v.s[i] += alpha * v.dsa[i]; v.z[i] += alpha * v.dza[i]; }
       for (int i = tid; i < e; i += NT) v.y[i] += alpha * v.dya[i];
       __syncthreads();
+      prof_lap(c, PH_STEP);
     }
     if (tid == 0) { a.status[sc] = status; a.iters[sc] = it; if (a.resid) a.resid[sc] = best; }
     __syncthreads();
@@ -343,37 +624,41 @@ struct BwdArgs {
   T *dQ, *dp, *dG, *dh, *dA, *db, *dF;
   unsigned flags;
   T* ws;
+  const T* Rsave;             // nullptr (recompute R) or the matrices saved by the forward pass
+  long long* prof;
 };
 
-template <typename T>
-__global__ void __launch_bounds__(512) lcp_backward_kernel(const BwdArgs<T> a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* sm = reinterpret_cast<T*>(smem_raw);
+template <typename T, int MODE>
+__global__ void __launch_bounds__(512, 1) lcp_backward_kernel(const BwdArgs<T> a) {
+  T* sm = smem_base<T>();
   __shared__ int flag;
   __shared__ int lu_flag_s;
   const Plan& P = a.P;
   const int n = P.n, m = P.m, e = P.e, tid = threadIdx.x, NT = blockDim.x;
-  SceneCtx<T> c;
-  setup_ctx(c, P, sm, a.ws + (size_t)blockIdx.x * P.ws_per_cta);
-  c.lu_flag = &lu_flag_s;
-  Vecs<T>& v = c.v;
+  SceneCtx<T, MODE> c;
+  setup_ctx<T, MODE>(c, P, sm, a.ws + (size_t)blockIdx.x * P.ws_per_cta, &lu_flag_s, a.prof);
+  Vecs<T> v = c.vecs();
+  T* const sb = sm;
+  auto off = [&](const T* p_) { return (int)(p_ - sb); };
 
   for (int sc = blockIdx.x; sc < a.B; sc += gridDim.x) {
+    prof_start(c);
     bind_scene(c, P, sm, a.Q + (size_t)sc * n * n, a.G + (size_t)sc * m * n,
                e > 0 ? a.A + (size_t)sc * e * n : nullptr, a.F + (size_t)sc * m * m);
     const T* zh = a.zhat + (size_t)sc * n;
     const T* lam = a.lam + (size_t)sc * m;
     const T* slk = a.slack + (size_t)sc * m;
     const T* nu = e > 0 ? a.nu + (size_t)sc * e : nullptr;
+    if (a.Rsave) { c.R = const_cast<T*>(a.Rsave) + (size_t)sc * m * m; c.Rsaved = true; }
     prefactor(c, &flag);     // singular Q was already reported by the forward pass
-    // stage saved vectors in shared memory
+    prof_lap(c, PH_PREFACTOR);
     for (int i = tid; i < n; i += NT) { v.x[i] = zh[i]; v.rx[i] = a.g[(size_t)sc * n + i]; }
     for (int i = tid; i < m; i += NT) { v.z[i] = lam[i]; v.s[i] = slk[i]; v.d[i] = lam[i] / slk[i]; v.rs2[i] = T(0); }   // :44
     for (int i = tid; i < e; i += NT) v.y[i] = nu[i];
     __syncthreads();
-    factor_kkt(c, v.d);                                            // :46
-    // :47-50  solve_kkt(rx = dl_dzhat, rs = 0, rz = 0, ry = 0)
-    solve_kkt(c, v.d, v.rx, v.rs2, (const T*)nullptr, (const T*)nullptr, v.dxa, v.dsa, v.dza, v.dya);
+    factor_kkt(c);                                            // :46
+    solve_kkt(c, off(v.rx), off(v.rs2), -1, -1, off(v.dxa), off(v.dsa), off(v.dza), off(v.dya));   // :47-50
+    prof_lap(c, PH_SOLVE);
     const T* dx = v.dxa; const T* dlam = v.dza; const T* dnu = v.dya;
     if (a.dp) for (int i = tid; i < n; i += NT) a.dp[(size_t)sc * n + i] = dx[i];                       // :52
     if (a.dh) for (int i = tid; i < m; i += NT) a.dh[(size_t)sc * m + i] = -dlam[i];                    // :55
@@ -395,6 +680,7 @@ __global__ void __launch_bounds__(512) lcp_backward_kernel(const BwdArgs<T> a) {
       for (int t = tid; t < n * n; t += NT) { int i = t / n, j = t - i * n; o[t] = T(0.5) * (dx[i] * v.x[j] + v.x[i] * dx[j]); }
     }
     __syncthreads();
+    prof_lap(c, PH_STEP);
   }
 }
 

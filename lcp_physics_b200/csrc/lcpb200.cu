@@ -9,7 +9,7 @@
 
 #include "../../include/lcpb200.h"
 #include "lcp_assemble.cuh"
-#include "lcp_solver.cuh"
+#include "lcp_launch.h"
 
 using namespace lcpb200;
 
@@ -48,55 +48,91 @@ struct lcpb200_handle_s {
   // host-buffer pipeline state
   cudaStream_t streams[NSLOT] = {nullptr, nullptr};
   DevBuf d_in[7], d_out[6], d_bwd[16];
+  long long* prof = nullptr;      // optional per-CTA phase cycle counters [NSLOT*max_grid][PH_COUNT]
+  DevBuf d_R;                     // host pipeline: R of every scene, kept for backward_host
+  int retained_B = 0;             // scenes whose inputs/results/R forward_host left on the device
 };
+
+static int pad_ld(int cols, int elem_bytes) {
+  // leading dimension (elements): >= cols, a multiple of the 16-byte vector, and == 4 (mod 32) in
+  // 32-bit words so that 4 consecutive rows tile all 32 banks (lcp_lu.cuh)
+  const int wpe = elem_bytes / 4;             // words per element
+  int ld = cols;
+  while ((ld * wpe) % 32 != 4 || (ld * elem_bytes) % 16 != 0) ++ld;
+  return ld;
+}
 
 template <typename T>
 static int make_plan(lcpb200_handle_s* h) {
   Plan& P = h->plan;
   const int n = h->n, m = h->m, e = h->e;
+  constexpr int NB = Blk<T>::NB, VC = VecOf<T>::VC;
+  const int w = (int)sizeof(T);
   memset(&P, 0, sizeof(P));
   P.n = n; P.m = m; P.e = e;
-  P.nt = (m >= 96 || n >= 96) ? 512 : (m >= 32 ? 256 : 128);
+  P.mp = ((m + NB - 1) / NB) * NB;
+  const int mp = P.mp;
+  P.nt = (mp >= 96 || n >= 96) ? 512 : (mp >= 64 ? 256 : 128);
   Vecs<T> vv;
-  const long long vec_elems = vv.carve(nullptr, n, m, e, P.nt);
-  long long budget = (long long)h->smem_optin - 1024 - vec_elems * (long long)sizeof(T);
+  const long long vec_elems = vv.carve(nullptr, n, mp, e, P.nt);
+  long long budget = (long long)h->smem_optin - 1024 - vec_elems * w;   // bytes
   if (budget < 0) return fail("problem too large: the shared-memory vectors alone exceed the per-CTA limit");
-  long long off = 0;
   auto al4 = [](long long x) { return (x + 3) & ~3LL; };
-  P.ldT = m | 1;
+  long long off = 0;
+  // ---- residency of T
+  const int ldfull = pad_ld(mp, w);
+  if ((long long)mp * ldfull * w <= budget) {
+    P.mode = 0; P.m1 = mp; P.ldT = ldfull; P.ldL = 0;
+    P.off_T = (int)off; off += al4((long long)mp * ldfull);
+  } else {
+    const int m1 = (((mp / 2) + NB - 1) / NB) * NB, n2 = mp - m1;
+    const int ldl = pad_ld(m1, w);
+    const int tiles = ((n2 + 15) / 16) * ((n2 + 16 * VC - 1) / (16 * VC));
+    const long long need = ((long long)m1 * ldfull + (long long)n2 * ldl) * w;
+    if (n2 > 0 && n2 <= m1 && need <= budget && tiles <= P.nt / 32) {
+      P.mode = 1; P.m1 = m1; P.ldT = ldfull; P.ldL = ldl;
+      P.off_T = (int)off; off += al4((long long)m1 * ldfull);
+      P.off_L = (int)off; off += al4((long long)n2 * ldl);
+    } else {
+      P.mode = 2; P.m1 = mp; P.ldT = ((mp + VC - 1) / VC) * VC; P.ldL = 0;
+    }
+  }
+  P.stage_ld = 0;
+  if (P.mode != 2) {
+    const int lds = pad_ld(n, w);
+    if ((long long)m * lds <= (long long)P.m1 * P.ldT) P.stage_ld = lds;
+  }
+  budget -= off * w;
   P.ldG = n;
-  P.ldQi = n | 1;
-  const long long Tb = al4((long long)m * P.ldT), Gb = al4((long long)m * P.ldG), Qb = al4((long long)n * P.ldQi);
-  if (Tb * (long long)sizeof(T) <= budget) { P.T_smem = 1; P.off_T = (int)off; off += Tb; budget -= Tb * sizeof(T); }
-  if (Gb * (long long)sizeof(T) <= budget) { P.G_smem = 1; P.off_G = (int)off; off += Gb; budget -= Gb * sizeof(T); }
-  if (Qb * (long long)sizeof(T) <= budget) { P.Qi_smem = 1; P.off_Qi = (int)off; off += Qb; budget -= Qb * sizeof(T); }
+  P.ldQi = ((n + VC - 1) / VC) * VC;
+  const long long Gb = al4((long long)m * P.ldG), Qb = al4((long long)n * P.ldQi);
+  if (Gb * w <= budget) { P.G_smem = 1; P.off_G = (int)off; off += Gb; budget -= Gb * w; }
+  if (Qb * w <= budget) { P.Qi_smem = 1; P.off_Qi = (int)off; off += Qb; budget -= Qb * w; }
   P.off_vec = (int)off;
-  P.smem_bytes = (int)((off + vec_elems) * sizeof(T));
-  long long w = 0;
-  P.w_Qi = w; w += Qb;
-  P.w_R = w; w += al4((long long)m * m);
-  P.w_T = w; w += Tb;
-  P.w_X = w; w += al4((long long)n * m);
-  P.w_XA = w; w += al4((long long)n * e);
-  P.w_S11 = w; w += al4((long long)e * e);
-  P.w_V = w; w += al4((long long)m * e);
-  P.w_W = w; w += al4((long long)e * m);
-  P.ws_per_cta = w;
+  P.smem_bytes = (int)((off + vec_elems) * w);
+  long long ws = 0;
+  P.w_Qi = ws; ws += Qb;
+  P.w_R = ws; ws += al4((long long)m * m);
+  P.w_T = ws; ws += (P.mode == 2) ? al4((long long)mp * P.ldT) : 0;
+  P.w_U12 = ws; ws += (P.mode == 1) ? al4((long long)P.m1 * (mp - P.m1)) : 0;
+  P.w_X = ws; ws += al4((long long)n * m);
+  P.w_XA = ws; ws += al4((long long)n * e);
+  P.w_S11 = ws; ws += al4((long long)e * e);
+  P.w_V = ws; ws += al4((long long)m * e);
+  P.w_W = ws; ws += al4((long long)e * m);
+  P.ws_per_cta = ws;
   return 0;
 }
 
 template <typename T>
 static int configure_kernels(lcpb200_handle_s* h) {
   const Plan& P = h->plan;
-  // The attribute is per kernel, not per handle: always raise it to the device maximum so that
-  // handles with different plans can coexist.
   const int dyn_max = h->smem_optin - 1024;
-  CK(cudaFuncSetAttribute(lcp_forward_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
-  CK(cudaFuncSetAttribute(lcp_backward_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
-  int occ_f = 0, occ_b = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, lcp_forward_kernel<T>, P.nt, P.smem_bytes));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, lcp_backward_kernel<T>, P.nt, P.smem_bytes));
-  int occ = std::min(occ_f, occ_b);
+  int occ = 0;
+  cudaError_t ce = P.mode == 0 ? configure_t<T, 0>(P.nt, P.smem_bytes, dyn_max, &occ)
+                 : P.mode == 1 ? configure_t<T, 1>(P.nt, P.smem_bytes, dyn_max, &occ)
+                               : configure_t<T, 2>(P.nt, P.smem_bytes, dyn_max, &occ);
+  if (ce != cudaSuccess) return fail(std::string("kernel configuration: ") + cudaGetErrorString(ce));
   if (occ < 1) return fail("kernel cannot be resident with the planned shared memory");
   occ = std::min(occ, 8);
   h->max_grid = occ * h->num_sms;
@@ -137,10 +173,12 @@ extern "C" int lcpb200_destroy(lcpb200_handle_t h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   if (h->ws) cudaFree(h->ws);
+  if (h->prof) cudaFree(h->prof);
   for (auto& s : h->streams) if (s) cudaStreamDestroy(s);
   for (auto& b : h->d_in) b.release();
   for (auto& b : h->d_out) b.release();
   for (auto& b : h->d_bwd) b.release();
+  h->d_R.release();
   delete h;
   return 0;
 }
@@ -150,12 +188,13 @@ extern "C" size_t lcpb200_workspace_bytes(lcpb200_handle_t h) { return h ? h->ws
 extern "C" int lcpb200_describe(lcpb200_handle_t h, char* buf, size_t len) {
   if (!h || !buf) return fail("null argument");
   const Plan& P = h->plan;
+  static const char* modes[3] = {"smem", "smem-split(U12 in L2)", "L2"};
   snprintf(buf, len,
-           "dtype=%s n=%d m=%d e=%d threads=%d smem=%dB (T:%s G:%s Qinv:%s) ldT=%d grid<=%d "
+           "dtype=%s n=%d m=%d(pad %d) e=%d threads=%d smem=%dB T:%s m1=%d ldT=%d ldL=%d G:%s Qinv:%s grid<=%d "
            "ws/CTA=%lldB sms=%d",
-           h->dtype == LCPB200_F32 ? "f32" : "f64", P.n, P.m, P.e, P.nt, P.smem_bytes,
-           P.T_smem ? "smem" : "L2", P.G_smem ? "smem" : "L2", P.Qi_smem ? "smem" : "L2", P.ldT,
-           h->max_grid, (long long)(P.ws_per_cta * (h->dtype == LCPB200_F32 ? 4 : 8)), h->num_sms);
+           h->dtype == LCPB200_F32 ? "f32" : "f64", P.n, P.m, P.mp, P.e, P.nt, P.smem_bytes, modes[P.mode], P.m1,
+           P.ldT, P.ldL, P.G_smem ? "smem" : "L2", P.Qi_smem ? "smem" : "L2", h->max_grid,
+           (long long)(P.ws_per_cta * (h->dtype == LCPB200_F32 ? 4 : 8)), h->num_sms);
   return 0;
 }
 
@@ -163,7 +202,7 @@ template <typename T>
 static int launch_forward(lcpb200_handle_s* h, int slot, int B, const void* Q, const void* p, const void* G,
                           const void* hv, const void* A, const void* b, const void* F, double eps,
                           int not_improved_lim, int max_iter, void* zhat, void* nu, void* lam, void* slack,
-                          int32_t* status, int32_t* iters, void* resid, cudaStream_t st) {
+                          int32_t* status, int32_t* iters, void* resid, void* Rsave, cudaStream_t st) {
   FwdArgs<T> a;
   a.P = h->plan;
   a.B = B;
@@ -172,10 +211,15 @@ static int launch_forward(lcpb200_handle_s* h, int slot, int B, const void* Q, c
   a.zhat = (T*)zhat; a.nu = (T*)nu; a.lam = (T*)lam; a.slack = (T*)slack; a.resid = (T*)resid;
   a.status = status; a.iters = iters;
   a.eps = (T)eps; a.not_improved_lim = not_improved_lim; a.max_iter = max_iter;
+  a.Rsave = (T*)Rsave;
   a.ws = (T*)h->ws + (size_t)slot * h->plan.ws_per_cta * h->max_grid;
+  a.prof = h->prof ? h->prof + (size_t)slot * h->max_grid * PH_COUNT : nullptr;
   const int grid = std::min(B, h->max_grid);
-  lcp_forward_kernel<T><<<grid, h->plan.nt, h->plan.smem_bytes, st>>>(a);
-  CK(cudaGetLastError());
+  const int mode = h->plan.mode;
+  const cudaError_t le = mode == 0   ? launch_forward_t<T, 0>(a, grid, st)
+                         : mode == 1 ? launch_forward_t<T, 1>(a, grid, st)
+                                     : launch_forward_t<T, 2>(a, grid, st);
+  CK(le);
   return 0;
 }
 
@@ -183,7 +227,7 @@ template <typename T>
 static int launch_backward(lcpb200_handle_s* h, int slot, int B, const void* Q, const void* G, const void* A,
                            const void* F, const void* zhat, const void* nu, const void* lam, const void* slack,
                            const void* g, void* dQ, void* dp, void* dG, void* dh, void* dA, void* db, void* dF,
-                           unsigned flags, cudaStream_t st) {
+                           const void* Rsave, unsigned flags, cudaStream_t st) {
   BwdArgs<T> a;
   a.P = h->plan;
   a.B = B;
@@ -192,10 +236,15 @@ static int launch_backward(lcpb200_handle_s* h, int slot, int B, const void* Q, 
   a.g = (const T*)g;
   a.dQ = (T*)dQ; a.dp = (T*)dp; a.dG = (T*)dG; a.dh = (T*)dh; a.dA = (T*)dA; a.db = (T*)db; a.dF = (T*)dF;
   a.flags = flags;
+  a.Rsave = (const T*)Rsave;
   a.ws = (T*)h->ws + (size_t)slot * h->plan.ws_per_cta * h->max_grid;
+  a.prof = h->prof ? h->prof + (size_t)slot * h->max_grid * PH_COUNT : nullptr;
   const int grid = std::min(B, h->max_grid);
-  lcp_backward_kernel<T><<<grid, h->plan.nt, h->plan.smem_bytes, st>>>(a);
-  CK(cudaGetLastError());
+  const int mode = h->plan.mode;
+  const cudaError_t le = mode == 0   ? launch_backward_t<T, 0>(a, grid, st)
+                         : mode == 1 ? launch_backward_t<T, 1>(a, grid, st)
+                                     : launch_backward_t<T, 2>(a, grid, st);
+  CK(le);
   return 0;
 }
 
@@ -216,22 +265,22 @@ static int check_fwd_args(lcpb200_handle_t h, int B, const void* Q, const void* 
 extern "C" int lcpb200_forward(lcpb200_handle_t h, int B, const void* Q, const void* p, const void* G,
                                const void* hv, const void* A, const void* b, const void* F, double eps,
                                int not_improved_lim, int max_iter, void* zhat, void* nu, void* lam, void* slack,
-                               int32_t* status, int32_t* iters, void* resid, void* stream) {
+                               int32_t* status, int32_t* iters, void* resid, void* Rsave, void* stream) {
   if (int rc = check_fwd_args(h, B, Q, p, G, hv, A, b, F, zhat, nu, lam, slack, status, iters, max_iter)) return rc;
   if (B == 0) return 0;
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   return h->dtype == LCPB200_F32
              ? launch_forward<float>(h, 0, B, Q, p, G, hv, A, b, F, eps, not_improved_lim, max_iter, zhat, nu, lam,
-                                     slack, status, iters, resid, st)
+                                     slack, status, iters, resid, Rsave, st)
              : launch_forward<double>(h, 0, B, Q, p, G, hv, A, b, F, eps, not_improved_lim, max_iter, zhat, nu, lam,
-                                      slack, status, iters, resid, st);
+                                      slack, status, iters, resid, Rsave, st);
 }
 
 extern "C" int lcpb200_backward(lcpb200_handle_t h, int B, const void* Q, const void* G, const void* A,
                                 const void* F, const void* zhat, const void* nu, const void* lam,
                                 const void* slack, const void* g, void* dQ, void* dp, void* dG, void* dh, void* dA,
-                                void* db, void* dF, unsigned flags, void* stream) {
+                                void* db, void* dF, const void* Rsave, unsigned flags, void* stream) {
   if (!h) return fail("null handle");
   if (B < 0) return fail("B < 0");
   if (!Q || !G || !F || !zhat || !lam || !slack || !g) return fail("Q, G, F, zhat, lam, slack, dl_dzhat must be non-NULL");
@@ -242,8 +291,29 @@ extern "C" int lcpb200_backward(lcpb200_handle_t h, int B, const void* Q, const 
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   return h->dtype == LCPB200_F32
-             ? launch_backward<float>(h, 0, B, Q, G, A, F, zhat, nu, lam, slack, g, dQ, dp, dG, dh, dA, db, dF, flags, st)
-             : launch_backward<double>(h, 0, B, Q, G, A, F, zhat, nu, lam, slack, g, dQ, dp, dG, dh, dA, db, dF, flags, st);
+             ? launch_backward<float>(h, 0, B, Q, G, A, F, zhat, nu, lam, slack, g, dQ, dp, dG, dh, dA, db, dF, Rsave, flags, st)
+             : launch_backward<double>(h, 0, B, Q, G, A, F, zhat, nu, lam, slack, g, dQ, dp, dG, dh, dA, db, dF, Rsave, flags, st);
+}
+
+extern "C" int lcpb200_profile(lcpb200_handle_t h, int enable, long long* out) {
+  // Development aid: per-phase SM cycle counters (thread 0 of every CTA), summed over CTAs.
+  // enable = 1 allocates + zeroes the counters, 0 frees them; `out` (PH_COUNT = 6 values:
+  // prefactor, load T, LU, KKT solves, residuals, step rules) receives the current sums.
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->device));
+  const size_t cnt = (size_t)lcpb200_handle_s::NSLOT * h->max_grid * PH_COUNT;
+  if (out) {
+    for (int i = 0; i < PH_COUNT; ++i) out[i] = 0;
+    if (h->prof) {
+      std::vector<long long> tmp(cnt);
+      CK(cudaMemcpy(tmp.data(), h->prof, cnt * sizeof(long long), cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < cnt; ++i) out[i % PH_COUNT] += tmp[i];
+    }
+  }
+  if (enable && !h->prof) CK(cudaMalloc(&h->prof, cnt * sizeof(long long)));
+  if (enable) CK(cudaMemset(h->prof, 0, cnt * sizeof(long long)));
+  if (!enable && h->prof) { cudaFree(h->prof); h->prof = nullptr; }
+  return 0;
 }
 
 // ------------------------------------------------------------------ host-buffer pipeline
@@ -280,6 +350,9 @@ extern "C" int lcpb200_forward_host(lcpb200_handle_t h, int B, const void* Q, co
   for (int i = 0; i < 6; ++i) if (out_sz[i]) CK(h->d_out[i].ensure(out_sz[i] * B));
   DevBuf& d_resid = h->d_bwd[15];
   if (resid) CK(d_resid.ensure(w * B));
+  h->retained_B = 0;
+  const bool keepR = (m * m * w * (size_t)B) <= ((size_t)8 << 30);      // keep R for backward_host (<= 8 GiB)
+  if (keepR) CK(h->d_R.ensure(m * m * w * (size_t)B));
   const int C = chunk_scenes(h, B);
   int k = 0;
   for (int s0 = 0; s0 < B; s0 += C, ++k) {
@@ -298,14 +371,16 @@ extern "C" int lcpb200_forward_host(lcpb200_handle_t h, int B, const void* Q, co
                                          max_iter, at(h->d_out[0], out_sz[0]), at(h->d_out[1], out_sz[1]),
                                          at(h->d_out[2], out_sz[2]), at(h->d_out[3], out_sz[3]),
                                          (int32_t*)at(h->d_out[4], 4), (int32_t*)at(h->d_out[5], 4),
-                                         resid ? (char*)d_resid.p + w * s0 : nullptr, st)
+                                         resid ? (char*)d_resid.p + w * s0 : nullptr,
+                                         keepR ? (char*)h->d_R.p + m * m * w * s0 : nullptr, st)
                  : launch_forward<double>(h, slot, cb, at(h->d_in[0], in_sz[0]), at(h->d_in[1], in_sz[1]),
                                           at(h->d_in[2], in_sz[2]), at(h->d_in[3], in_sz[3]), at(h->d_in[4], in_sz[4]),
                                           at(h->d_in[5], in_sz[5]), at(h->d_in[6], in_sz[6]), eps, not_improved_lim,
                                           max_iter, at(h->d_out[0], out_sz[0]), at(h->d_out[1], out_sz[1]),
                                           at(h->d_out[2], out_sz[2]), at(h->d_out[3], out_sz[3]),
                                           (int32_t*)at(h->d_out[4], 4), (int32_t*)at(h->d_out[5], 4),
-                                          resid ? (char*)d_resid.p + w * s0 : nullptr, st);
+                                          resid ? (char*)d_resid.p + w * s0 : nullptr,
+                                          keepR ? (char*)h->d_R.p + m * m * w * s0 : nullptr, st);
     if (rc) return rc;
     for (int i = 0; i < 6; ++i)
       if (out_sz[i] && out_dst[i])
@@ -315,6 +390,7 @@ extern "C" int lcpb200_forward_host(lcpb200_handle_t h, int B, const void* Q, co
       CK(cudaMemcpyAsync((char*)resid + w * s0, (char*)d_resid.p + w * s0, w * cb, cudaMemcpyDeviceToHost, st));
   }
   for (auto& s : h->streams) CK(cudaStreamSynchronize(s));
+  h->retained_B = keepR ? B : 0;
   return 0;
 }
 
@@ -324,8 +400,16 @@ extern "C" int lcpb200_backward_host(lcpb200_handle_t h, int B, const void* Q, c
                                      void* dA, void* db, void* dF, unsigned flags) {
   if (!h) return fail("null handle");
   if (B < 0) return fail("B < 0");
-  if (!Q || !G || !F || !zhat || !lam || !slack || !g) return fail("Q, G, F, zhat, lam, slack, dl_dzhat must be non-NULL");
-  if (h->e > 0 && (!A || !nu)) return fail("A and nu must be non-NULL when e > 0");
+  // Q == NULL: reuse the device copies (inputs, results and R) that the last forward_host on this
+  // handle left behind -- the save_for_backward of lcp.py:34 without a second upload.
+  const bool retained = (Q == nullptr);
+  if (retained) {
+    if (h->retained_B != B || B == 0) return fail("backward_host: no retained forward state for this batch");
+    if (!g) return fail("dl_dzhat must be non-NULL");
+  } else {
+    if (!G || !F || !zhat || !lam || !slack || !g) return fail("Q, G, F, zhat, lam, slack, dl_dzhat must be non-NULL");
+    if (h->e > 0 && (!A || !nu)) return fail("A and nu must be non-NULL when e > 0");
+  }
   if (flags != LCPB200_BWD_BUG_COMPATIBLE) return fail("only LCPB200_BWD_BUG_COMPATIBLE is implemented");
   if (B == 0) return 0;
   CK(cudaSetDevice(h->device));
@@ -336,13 +420,17 @@ extern "C" int lcpb200_backward_host(lcpb200_handle_t h, int B, const void* Q, c
   const size_t in_sz[9] = {n * n * w, m * n * w, e * n * w, m * m * w, n * w, e * w, m * w, m * w, n * w};
   const void* in_src[9] = {Q, G, A, F, zhat, nu, lam, slack, g};
   // Q, G, A, F may already be resident from forward_host (same buffers d_in[0,2,4,6]); we re-copy for safety.
-  DevBuf* in_buf[9] = {&h->d_in[0], &h->d_in[2], &h->d_in[4], &h->d_in[6], &h->d_bwd[0], &h->d_bwd[1],
-                       &h->d_bwd[2], &h->d_bwd[3], &h->d_bwd[4]};
+  // retained: zhat/nu/lam/slack live in the forward's result buffers d_out[0..3]
+  DevBuf* in_buf[9] = {&h->d_in[0], &h->d_in[2], &h->d_in[4], &h->d_in[6],
+                       retained ? &h->d_out[0] : &h->d_bwd[0], retained ? &h->d_out[1] : &h->d_bwd[1],
+                       retained ? &h->d_out[2] : &h->d_bwd[2], retained ? &h->d_out[3] : &h->d_bwd[3], &h->d_bwd[4]};
+  const bool resident[9] = {retained, retained, retained, retained, retained, retained, retained, retained, false};
   const size_t out_sz[7] = {n * n * w, n * w, m * n * w, m * w, e * n * w, e * w, m * m * w};
   void* out_dst[7] = {dQ, dp, dG, dh, dA, db, dF};
   DevBuf* out_buf[7] = {&h->d_bwd[5], &h->d_bwd[6], &h->d_bwd[7], &h->d_bwd[8], &h->d_bwd[9], &h->d_bwd[10],
                         &h->d_bwd[11]};
-  for (int i = 0; i < 9; ++i) if (in_sz[i] && in_src[i]) CK(in_buf[i]->ensure(in_sz[i] * B));
+  if (!retained) h->retained_B = 0;       // the input buffers are about to be overwritten
+  for (int i = 0; i < 9; ++i) if (in_sz[i] && (in_src[i] || resident[i])) CK(in_buf[i]->ensure(in_sz[i] * B));
   for (int i = 0; i < 7; ++i) if (out_sz[i] && out_dst[i]) CK(out_buf[i]->ensure(out_sz[i] * B));
   const int C = chunk_scenes(h, B);
   int k = 0;
@@ -351,16 +439,19 @@ extern "C" int lcpb200_backward_host(lcpb200_handle_t h, int B, const void* Q, c
     const int slot = k % lcpb200_handle_s::NSLOT;
     cudaStream_t st = h->streams[slot];
     for (int i = 0; i < 9; ++i)
-      if (in_sz[i] && in_src[i])
+      if (in_sz[i] && in_src[i] && !resident[i])
         CK(cudaMemcpyAsync((char*)in_buf[i]->p + in_sz[i] * s0, (const char*)in_src[i] + in_sz[i] * s0,
                            in_sz[i] * cb, cudaMemcpyHostToDevice, st));
-    auto ai = [&](int i) -> void* { return (in_sz[i] && in_src[i]) ? (char*)in_buf[i]->p + in_sz[i] * s0 : nullptr; };
+    auto ai = [&](int i) -> void* {
+      return (in_sz[i] && (in_src[i] || resident[i])) ? (char*)in_buf[i]->p + in_sz[i] * s0 : nullptr;
+    };
+    const void* rs = retained ? (const char*)h->d_R.p + m * m * w * s0 : nullptr;
     auto ao = [&](int i) -> void* { return (out_sz[i] && out_dst[i]) ? (char*)out_buf[i]->p + out_sz[i] * s0 : nullptr; };
     int rc = h->dtype == LCPB200_F32
                  ? launch_backward<float>(h, slot, cb, ai(0), ai(1), ai(2), ai(3), ai(4), ai(5), ai(6), ai(7), ai(8),
-                                          ao(0), ao(1), ao(2), ao(3), ao(4), ao(5), ao(6), flags, st)
+                                          ao(0), ao(1), ao(2), ao(3), ao(4), ao(5), ao(6), rs, flags, st)
                  : launch_backward<double>(h, slot, cb, ai(0), ai(1), ai(2), ai(3), ai(4), ai(5), ai(6), ai(7), ai(8),
-                                           ao(0), ao(1), ao(2), ao(3), ao(4), ao(5), ao(6), flags, st);
+                                           ao(0), ao(1), ao(2), ao(3), ao(4), ao(5), ao(6), rs, flags, st);
     if (rc) return rc;
     for (int i = 0; i < 7; ++i)
       if (out_sz[i] && out_dst[i])

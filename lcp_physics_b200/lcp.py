@@ -58,10 +58,13 @@ def _stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def solve_forward(Q, p, G, h, A, b, F, eps=1e-12, not_improved_lim=3, max_iter=10, out=None):
+def solve_forward(Q, p, G, h, A, b, F, eps=1e-12, not_improved_lim=3, max_iter=10, out=None, save=None):
     """Raw forward: returns (zhat, nus, lams, slacks, status, iters, resid).
     All inputs on one device (CUDA or CPU), same dtype. `out` may hold preallocated
-    result tensors (same order; pinned host tensors make the host path's D2H fast)."""
+    result tensors (same order; pinned host tensors make the host path's D2H fast).
+    `save`: a dict that receives what the backward can reuse -- for CUDA inputs the
+    per-scene Schur matrix R ("R"); for CPU inputs a token of the state the library
+    retained on the device ("token")."""
     _lib.require_cuda()
     lib = _lib.load()
     B, n, m, e = _sizes(Q, p, G, h, A, b, F)
@@ -88,16 +91,26 @@ def solve_forward(Q, p, G, h, A, b, F, eps=1e-12, not_improved_lim=3, max_iter=1
     args = [hd.raw, B] + [_lib.ptr(t) for t in ins] + [float(eps), int(not_improved_lim), int(max_iter)] + \
            [_lib.ptr(t) for t in (zhat, nu, lam, slack, status, iters, resid)]
     if on_host:
+        hd.host_generation += 1
         _lib.check(lib.lcpb200_forward_host(*args))
+        if save is not None:
+            save["token"] = (hd, hd.host_generation, B)
     else:
+        R = None
+        if save is not None and B * m * m * Q.element_size() <= (8 << 30):
+            R = save.get("R_buffer")
+            if R is None or R.shape != (B, m, m) or R.dtype != dtype or R.device != dev:
+                R = torch.empty(B, m, m, dtype=dtype, device=dev)
+            save["R"] = R
         with torch.cuda.device(dev):
-            _lib.check(lib.lcpb200_forward(*args, _stream_ptr(dev)))
+            _lib.check(lib.lcpb200_forward(*args, _lib.ptr(R), _stream_ptr(dev)))
     return zhat, nu, lam, slack, status, iters, resid
 
 
-def solve_backward(Q, G, A, F, zhat, nu, lam, slack, dl_dzhat, need=(True,) * 7, out=None):
+def solve_backward(Q, G, A, F, zhat, nu, lam, slack, dl_dzhat, need=(True,) * 7, out=None, saved=None):
     """Raw backward (lcp.py:37-64): returns (dQ, dp, dG, dh, dA, db, dF); entries
-    not needed (or dA/db when e == 0) are None. `out`: preallocated results."""
+    not needed (or dA/db when e == 0) are None. `out`: preallocated results.
+    `saved`: the dict filled by solve_forward(save=...) for the same inputs."""
     _lib.require_cuda()
     lib = _lib.load()
     B, m, n = G.shape
@@ -120,10 +133,17 @@ def solve_backward(Q, G, A, F, zhat, nu, lam, slack, dl_dzhat, need=(True,) * 7,
     ins = [Q.contiguous(), G.contiguous(), A.contiguous() if e > 0 else None, F.contiguous(),
            zhat.contiguous(), nu.contiguous() if e > 0 else None, lam.contiguous(), slack.contiguous(),
            dl_dzhat.contiguous().to(dtype)]
-    args = [hd.raw, B] + [_lib.ptr(t) for t in ins] + [_lib.ptr(t) for t in outs] + [0]
     if on_host:
-        _lib.check(lib.lcpb200_backward_host(*args))
+        tok = saved.get("token") if saved else None
+        if tok is not None and tok[0] is hd and tok[1] == hd.host_generation and tok[2] == B:
+            in_ptrs = [None] * 8 + [_lib.ptr(ins[8])]          # reuse what forward_host left on the device
+        else:
+            in_ptrs = [_lib.ptr(t) for t in ins]
+        hd.host_generation += 1
+        _lib.check(lib.lcpb200_backward_host(hd.raw, B, *in_ptrs, *[_lib.ptr(t) for t in outs], 0))
     else:
+        R = saved.get("R") if saved else None
+        args = [hd.raw, B] + [_lib.ptr(t) for t in ins] + [_lib.ptr(t) for t in outs] + [_lib.ptr(R), 0]
         with torch.cuda.device(dev):
             _lib.check(lib.lcpb200_backward(*args, _stream_ptr(dev)))
     return tuple(outs)
@@ -132,8 +152,10 @@ def solve_backward(Q, G, A, F, zhat, nu, lam, slack, dl_dzhat, need=(True,) * 7,
 class _LCPFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Q, p, G, h, A, b, F, opts):
+        need_bwd = any(ctx.needs_input_grad[:7])
+        ctx.saved_state = {} if need_bwd else None
         zhat, nu, lam, slack, status, iters, resid = solve_forward(
-            Q, p, G, h, A, b, F, opts.eps, opts.not_improved_lim, opts.max_iter)
+            Q, p, G, h, A, b, F, opts.eps, opts.not_improved_lim, opts.max_iter, save=ctx.saved_state)
         if bool((status == _lib.STATUS_SINGULAR_Q).any()):
             raise RuntimeError(SINGULAR_Q_MSG)
         if opts.verbose >= 0 and bool((resid > 1.0).any()):
@@ -151,7 +173,8 @@ class _LCPFn(torch.autograd.Function):
     def backward(ctx, dl_dzhat):
         zhat, Q, G, A, F, nu, lam, slack = ctx.saved_tensors
         need = list(ctx.needs_input_grad[:7])
-        dQ, dp, dG, dh, dA, db, dF = solve_backward(Q, G, A, F, zhat, nu, lam, slack, dl_dzhat, need)
+        dQ, dp, dG, dh, dA, db, dF = solve_backward(Q, G, A, F, zhat, nu, lam, slack, dl_dzhat, need,
+                                                    saved=ctx.saved_state)
         return dQ, dp, dG, dh, dA, db, dF, None
 
 

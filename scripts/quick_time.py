@@ -9,20 +9,29 @@ def run(name, B, nb, nc, fd, e, dtype, reps=3, bwd=True):
     inp = tuple(t.cuda() for t in make_scenes(B, nb, nc, fd=fd, e=e, dtype=dtype, seed=0))
     n, m = 3 * nb, nc * (2 + fd)
     print(name, _lib.get_handle(dtype, n, m, e, 0).describe(), flush=True)
-    out = solve_forward(*inp, max_iter=10)
+    saved = {}
+    out = solve_forward(*inp, max_iter=10, save=saved)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     tf = tb = 0.0
     for _ in range(reps):
-        ev[0].record(); out = solve_forward(*inp, max_iter=10); ev[1].record()
+        ev[0].record(); out = solve_forward(*inp, max_iter=10, save=saved); ev[1].record()
         torch.cuda.synchronize(); tf += ev[0].elapsed_time(ev[1])
         if bwd:
             Q, p, G, h, A, b, F = inp
             g = torch.randn_like(out[0])
-            ev[2].record(); solve_backward(Q, G, A, F, out[0], out[1], out[2], out[3], g); ev[3].record()
+            ev[2].record(); solve_backward(Q, G, A, F, out[0], out[1], out[2], out[3], g, saved=saved); ev[3].record()
             torch.cuda.synchronize(); tb += ev[2].elapsed_time(ev[3])
     tf /= reps; tb /= reps
     it = out[5].float().mean().item()
+    hd = _lib.get_handle(dtype, n, m, e, 0)
+    hd.profile(True)
+    out = solve_forward(*inp, max_iter=10)
+    torch.cuda.synchronize()
+    pr = hd.profile(False)
+    tot = sum(pr.values()) or 1
+    ncta = min(B, 148)
+    print("  fwd phases (share, kcycles/scene): " + ", ".join("%s %.0f%% %.0fk" % (k, 100.0 * v / tot, v / B / 1e3) for k, v in pr.items()), flush=True)
     print("  %s B=%d fwd %.2f ms (%.0f solves/s) bwd %.2f ms  fwd+bwd %.0f solves/s  mean iters %.2f" %
           (name, B, tf, B / tf * 1e3, tb, B / (tf + tb) * 1e3, it), flush=True)
 
