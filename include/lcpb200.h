@@ -79,8 +79,10 @@ size_t lcpb200_workspace_bytes(lcpb200_handle_t h);
 int lcpb200_describe(lcpb200_handle_t h, char* buf, size_t len);
 
 /* Development aid: per-phase SM cycle counters of the solver kernels, summed over CTAs.
- * enable=1 allocates/zeroes them, 0 frees; out (may be NULL) receives 6 values:
- * {prefactor, load T, LU, KKT solves, residuals, step rules}. */
+ * enable=1 allocates/zeroes them, 0 frees; out (may be NULL) receives 12 values:
+ * {prefactor, load T, LU, KKT solves, residuals, step rules,
+ *  LU: diagonal blocks, LU: panel solves, LU: trailing updates, LU: diagonal-block inverses,
+ *  number of diagonal blocks that needed the pivoting fallback, number of diagonal blocks}. */
 int lcpb200_profile(lcpb200_handle_t h, int enable, long long* out);
 
 /* LCPFunction.forward. Outputs: zhat[B,n], nu[B,e] (NULL if e==0), lam[B,m],

@@ -1,16 +1,22 @@
 // lcp_lu.cuh -- blocked LU factorisation / solves of the m x m Schur matrix T, one CTA per scene.
 //
-// The matrix is held through a TView: rows [0,m1) in a `main` array (all mp columns), rows
-// [m1,mp) in a `low` array (columns [0,m1) only). When m1 == mp everything is in `main` (which may
-// be shared memory, or an L2-resident workspace for very large problems). When the full square
-// does not fit one CTA's shared memory (m = 256 fp32 is 256 KiB > 227 KiB) the planner picks
-// m1 = mp/2: the first m1 pivots are eliminated on the L-shaped region that IS resident, the
-// trailing block S22 = T22 - L21 U12 is accumulated in REGISTERS straight from the L2 copy of T22,
-// U12 (final by then) is spilled to an L2 workspace, S22 takes its place in `main`, and the second
-// half is factored there. Factors therefore live: L11\U11, L21, L22\U22 in shared memory, U12 in L2.
+// Storage (TView): rows [0,m1) in a `main` array (all mp columns), rows [m1,mp) in a `low` array
+// (columns [0,m1) only). MODE 0: m1 == mp, everything in shared memory. MODE 1 (split): the full
+// square does not fit one CTA's shared memory (m = 256 fp32 is 256 KiB > 227 KiB): m1 = mp/2, the
+// first m1 pivots are eliminated on the L-shaped region that IS resident, the trailing block
+// S22 = T22 - L21 U12 is accumulated in REGISTERS straight from the L2 copy of T22, U12 (final by
+// then) is spilled to an L2 workspace, S22 takes its place in `main`, and the second half is factored
+// there. Factors then live: L11\U11, L21, L22\U22 in shared memory, U12 in L2. MODE 2: `main` is an
+// L2-resident workspace (problems too large for either).
 //
 // mp is m padded to a multiple of NB with an identity block, so no partial blocks exist.
-// Pivoting: threshold partial pivoting restricted to each NB x NB diagonal block (lcp_device.cuh).
+// Pivoting: threshold partial pivoting restricted to each NB x NB diagonal block.
+//
+// Register discipline: with ~220 KB of shared memory carved out, L1 is a few KB, so a spilled
+// register costs an L2 round trip. Every heavy routine is therefore its own __noinline__ function
+// (own register allocation); matrices are passed as MPtr (shared-memory OFFSET, or a global pointer
+// in MODE 2) and vectors as offsets, so that inside each function the compiler can still prove the
+// accesses are to shared memory (LDS/STS with 32-bit addresses).
 #pragma once
 #include "lcp_device.cuh"
 
@@ -25,39 +31,53 @@ template <typename T> __device__ __forceinline__ void vec_get(const double2& v, 
 __device__ __forceinline__ float4 vec_make(const float (&o)[4]) { return make_float4(o[0], o[1], o[2], o[3]); }
 __device__ __forceinline__ double2 vec_make(const double (&o)[2]) { return make_double2(o[0], o[1]); }
 
-// All dynamic shared memory of the solver kernels. Declared at namespace scope so that every device
-// function (also non-inlined ones) can form pointers the compiler PROVES are shared (LDS/STS, 32-bit
-// addresses) instead of carrying generic 64-bit pointers through structs.
+// All dynamic shared memory of the solver kernels, at namespace scope so every device function can
+// form provably-shared pointers.
 extern __shared__ __align__(16) unsigned char lcpb200_smem[];
 template <typename T> __device__ __forceinline__ T* smem_base() { return reinterpret_cast<T*>(lcpb200_smem); }
+__device__ __forceinline__ int* smem_int(int o_i) { return reinterpret_cast<int*>(lcpb200_smem) + o_i; }
 
-// MODE 0: T fully in shared memory; 1: split (main + low in shared memory, U12 in L2); 2: T in L2.
+// Matrix base: shared-memory element offset (MODE 0/1) or global pointer (MODE 2).
+template <typename T, int MODE>
+struct MPtr {
+  long long off;          // elements relative to smem_base<T>() (may be negative after re-basing)
+  T* g;
+  __device__ __forceinline__ T* get() const { return MODE == 2 ? g : smem_base<T>() + off; }
+  __device__ __forceinline__ MPtr plus(long long d) const { MPtr r; r.off = off + d; r.g = g + d; return r; }
+};
+
 template <typename T, int MODE>
 struct TView {
-  int main_off, low_off;  // shared-memory offsets in elements (MODE 0/1)
-  T* main_g;              // L2 workspace (MODE 2)
+  MPtr<T, MODE> main_;    // rows [0,m1), columns [0,mp)
+  MPtr<T, 0> low_;        // rows [m1,mp), columns [0,m1)   (MODE 1 only, always shared)
   int ld, ldl;
   T* u12;                 // L2 spill of U12: [m1, mp-m1] row-major (MODE 1)
   int mp, m1;
-  // main: rows [0,m1), columns [0,mp);  low: rows [m1,mp), columns [0,m1)
-  __device__ __forceinline__ T* main() const { return MODE == 2 ? main_g : smem_base<T>() + main_off; }
-  __device__ __forceinline__ T* low() const { return smem_base<T>() + low_off; }
+  __device__ __forceinline__ T* main() const { return main_.get(); }
+  __device__ __forceinline__ T* low() const { return low_.get(); }
+};
+
+// Shared vectors used by the factorisation. *_i offsets are in 4-byte ints from the start of the
+// shared array, the others in elements of T.
+struct LuVec {
+  int o_perm_i, o_flag_i, o_rmaxs, o_rdiag, o_stage, lds;
 };
 
 // ---------------------------------------------------------------------------------------------
 // C[rows r_lo..r_hi) x [c_lo..c_hi)  -=  L[rows, k0..k0+NB) * U[k0..k0+NB, cols]   (rank-NB update)
+// C and the L panel live in the array `Cb` (row i at Cb + i*ldc), U in `Ub` (row k at Ub + k*ldu).
 // Thread tile TR x 2VC; warp tile (4 TR) x (16 VC): lane = (g = lane>>3, cg = lane&7) owns rows
 // rbase + g + 4 r and the two column vectors cbase + VC cg, cbase + 8 VC + VC cg, which makes the
 // L loads (vectors along k, 4 consecutive rows per instruction) and the U loads (128 contiguous
 // bytes per instruction, broadcast to the 4 row groups) bank-conflict-free for ld = 4 (mod 32) words.
-// rowsrc: functor i -> pointer to row i of the matrix holding BOTH the L panel and C.
-// urow:   functor k -> pointer to row k0+k of the matrix holding U (always `main`).
-template <typename T, int TR, typename RowFn>
-__device__ __forceinline__ void rank_nb_update(RowFn rowp, const T* __restrict__ Umain, int ldu, int k0,
-                                               int r_lo, int r_hi, int c_lo, int c_hi) {
+template <typename T, int CMODE, int UMODE, int TR>
+__device__ __noinline__ void rank_nb_update(MPtr<T, CMODE> Cb, int ldc, MPtr<T, UMODE> Ub, int ldu, int k0, int r_lo,
+                                            int r_hi, int c_lo, int c_hi) {
   using V = typename VecOf<T>::type;
   constexpr int VC = VecOf<T>::VC, NB = Blk<T>::NB;
   constexpr int WR = 4 * TR, WC = 16 * VC;
+  T* const C = Cb.get();
+  const T* const U = Ub.get();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int g = lane >> 3, cg = lane & 7;
   const int ntr = (r_hi - r_lo + WR - 1) / WR, ntc = (c_hi - c_lo + WC - 1) / WC;
@@ -66,14 +86,11 @@ __device__ __forceinline__ void rank_nb_update(RowFn rowp, const T* __restrict__
     const int rbase = r_lo + tr_ * WR + g;
     const int c0 = c_lo + tc_ * WC + VC * cg, c1 = c0 + 8 * VC;
     const bool v0 = c0 < c_hi, v1 = c1 < c_hi;
-    T* rp[TR];
-    bool rv[TR];
+    // rows beyond r_hi are clamped (their results are not stored)
+    T* const rp0 = C + (size_t)min(rbase, r_hi - 1) * ldc;
+    int roff[TR];
 #pragma unroll
-    for (int r = 0; r < TR; ++r) {
-      const int i = rbase + 4 * r;
-      rv[r] = i < r_hi;
-      rp[r] = rowp(rv[r] ? i : r_hi - 1);
-    }
+    for (int r = 0; r < TR; ++r) roff[r] = (min(rbase + 4 * r, r_hi - 1) - min(rbase, r_hi - 1)) * ldc;
     T acc[TR][2 * VC];
 #pragma unroll
     for (int r = 0; r < TR; ++r)
@@ -83,10 +100,10 @@ __device__ __forceinline__ void rank_nb_update(RowFn rowp, const T* __restrict__
     for (int kc = 0; kc < NB; kc += VC) {
       T l[TR][VC];
 #pragma unroll
-      for (int r = 0; r < TR; ++r) vec_get<T>(*reinterpret_cast<const V*>(rp[r] + k0 + kc), l[r]);
+      for (int r = 0; r < TR; ++r) vec_get<T>(*reinterpret_cast<const V*>(rp0 + roff[r] + k0 + kc), l[r]);
 #pragma unroll
       for (int kk = 0; kk < VC; ++kk) {
-        const T* ur = Umain + (size_t)(k0 + kc + kk) * ldu;
+        const T* ur = U + (size_t)(k0 + kc + kk) * ldu;
         T u[2 * VC];
         {
           T lo[VC], hi[VC];
@@ -103,74 +120,286 @@ __device__ __forceinline__ void rank_nb_update(RowFn rowp, const T* __restrict__
     }
 #pragma unroll
     for (int r = 0; r < TR; ++r) {
-      if (!rv[r]) continue;
+      if (rbase + 4 * r >= r_hi) continue;
+      T* rp = rp0 + roff[r];
       if (v0) {
         T cur[VC];
-        vec_get<T>(*reinterpret_cast<const V*>(rp[r] + c0), cur);
+        vec_get<T>(*reinterpret_cast<const V*>(rp + c0), cur);
 #pragma unroll
         for (int q = 0; q < VC; ++q) cur[q] -= acc[r][q];
-        *reinterpret_cast<V*>(rp[r] + c0) = vec_make(cur);
+        *reinterpret_cast<V*>(rp + c0) = vec_make(cur);
       }
       if (v1) {
         T cur[VC];
-        vec_get<T>(*reinterpret_cast<const V*>(rp[r] + c1), cur);
+        vec_get<T>(*reinterpret_cast<const V*>(rp + c1), cur);
 #pragma unroll
         for (int q = 0; q < VC; ++q) cur[q] -= acc[r][VC + q];
-        *reinterpret_cast<V*>(rp[r] + c1) = vec_make(cur);
+        *reinterpret_cast<V*>(rp + c1) = vec_make(cur);
       }
     }
   }
 }
 
 // Pick the thread-tile height so that the warp tiles roughly fill the CTA.
-template <typename T, typename RowFn>
-__device__ __forceinline__ void rank_nb_update_auto(RowFn rowp, const T* Umain, int ldu, int k0, int r_lo, int r_hi,
-                                                    int c_lo, int c_hi) {
+template <typename T, int CMODE, int UMODE>
+__device__ __forceinline__ void rank_nb_update_auto(MPtr<T, CMODE> Cb, int ldc, MPtr<T, UMODE> Ub, int ldu, int k0,
+                                                    int r_lo, int r_hi, int c_lo, int c_hi) {
   constexpr int VC = VecOf<T>::VC;
   if (r_hi <= r_lo || c_hi <= c_lo) return;
   const int nw = blockDim.x >> 5;
   const int ntc = (c_hi - c_lo + 16 * VC - 1) / (16 * VC);
   const int rows = r_hi - r_lo;
-  const int t8 = ((rows + 31) / 32) * ntc;
-  const int t4 = ((rows + 15) / 16) * ntc;
-  // rounds(t) * cost(tile): prefer the taller tile unless it leaves warps idle
-  const int c8 = ((t8 + nw - 1) / nw) * 8, c4 = ((t4 + nw - 1) / nw) * 4;
-  const int t2 = ((rows + 7) / 8) * ntc;
-  const int c2 = ((t2 + nw - 1) / nw) * 2;
-  if (c8 <= c4 && c8 <= c2) rank_nb_update<T, 8>(rowp, Umain, ldu, k0, r_lo, r_hi, c_lo, c_hi);
-  else if (c4 <= c2) rank_nb_update<T, 4>(rowp, Umain, ldu, k0, r_lo, r_hi, c_lo, c_hi);
-  else rank_nb_update<T, 2>(rowp, Umain, ldu, k0, r_lo, r_hi, c_lo, c_hi);
+  const int t8 = ((rows + 31) / 32) * ntc, t4 = ((rows + 15) / 16) * ntc, t2 = ((rows + 7) / 8) * ntc;
+  // rounds(t) * cost(tile); the constant models the per-tile load/store overhead
+  const int c8 = ((t8 + nw - 1) / nw) * 17, c4 = ((t4 + nw - 1) / nw) * 9, c2 = ((t2 + nw - 1) / nw) * 5;
+  if (c8 <= c4 && c8 <= c2) rank_nb_update<T, CMODE, UMODE, 8>(Cb, ldc, Ub, ldu, k0, r_lo, r_hi, c_lo, c_hi);
+  else if (c4 <= c2) rank_nb_update<T, CMODE, UMODE, 4>(Cb, ldc, Ub, ldu, k0, r_lo, r_hi, c_lo, c_hi);
+  else rank_nb_update<T, CMODE, UMODE, 2>(Cb, ldc, Ub, ldu, k0, r_lo, r_hi, c_lo, c_hi);
+}
+
+// Reciprocal off the slow IEEE-division path: hardware approximation + Newton steps (<= 1 ulp for
+// float, ~1 ulp for double); falls back to a true division outside the seed's range.
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(x));
+  const float r = fmaf(r0, fmaf(-x, r0, 1.0f), r0);
+  return (fabsf(r0) < INFINITY) ? r : r0;        // x == 0 / denormal: keep the infinity (no NaN)
+}
+__device__ __forceinline__ double fast_rcp(double x) {
+  float xf = (float)x, rf;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(xf));
+  if (!(fabsf(rf) < INFINITY) || rf == 0.0f) return 1.0 / x;     // outside the float range: exact path
+  double r = (double)rf;
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Diagonal block (NB x NB at D, leading dimension ld, in place), executed by ONE warp with lane i
-// owning row i IN MEMORY (no per-thread register arrays, run-time loops: ~1 KB of code, so this
-// single-warp dependent chain -- the critical path of the whole factorisation -- neither spills nor
-// thrashes the instruction cache; the fully unrolled shuffle version it replaces took 66k cycles
-// per block, 52% of the forward kernel, mostly in instruction-fetch and shuffle stalls).
-//   1. P_b L U  by right-looking elimination, reciprocal pivot scaling (getf2), threshold pivoting
-//      restricted to the rows of the block: the natural row is kept unless its pivot is below
-//      tau * (largest entry the row had when the block was loaded); only then the largest |entry|
-//      of the column among the remaining rows is swapped in (rows, scales and perm move together).
-//      Measured (DESIGN.md "Pivoting"): eager swaps inside a block HURT fp32 trajectory parity,
-//      never swapping leaves exact-zero pivots (0/0 -> NaN) on converged scenes.
-//   2. both triangular inverses in place and interleaved: inv(L) by ascending, inv(U) by
-//      descending right-looking substitution (row scaling of inv(U) deferred to the end).
-// Result: D = [strict-lower(inv L) \ upper(inv U)], perm[i] = source row of row i.
-// rmaxs: NB scratch elements (shared). Returns (warp-uniform) whether rows were interchanged.
-template <typename T, int NB>
-__device__ __forceinline__ bool diag_block_inplace(T* D, int ld, int* perm, T* rmaxs) {
+// Diagonal block, fast path (ONE warp): rows in REGISTERS, pivot rows broadcast by shuffles, fully
+// unrolled: the natural pivot order is taken speculatively and every pivot is checked against the
+// threshold rule (|pivot| >= tau * initial row scale, or else: it is the largest candidate of its
+// column inside the block); if a check fails NOTHING is written back and the caller runs the
+// pivoting routine below on the untouched block. The next
+// pivot's broadcast + reciprocal are issued right after the first column of the update, so their
+// latency hides behind the rest of the update (measured: 290 -> ~100 cycles per pivot).
+// On success: D = L\U in place, rdiag[j] = 1/U[j][j], perm = identity. Returns success (uniform).
+template <typename T, int MODE, int NB>
+__device__ __noinline__ bool diag_lu_regs(MPtr<T, MODE> Db, int ld, int o_perm_i, int o_rdiag) {
   using V = typename VecOf<T>::type;
-  constexpr int VC = VecOf<T>::VC;
+  constexpr int VC = VecOf<T>::VC, NV = NB / VC;
+  T* const D = Db.get();
+  const int lane = threadIdx.x & 31;
+  const int li = lane < NB ? lane : NB - 1;      // lanes >= NB mirror the last row and never store
+  T* row = D + (size_t)li * ld;
+  T a[NB];
+  T rm = 0;
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    T t[VC];
+    vec_get<T>(*reinterpret_cast<const V*>(row + c * VC), t);
+#pragma unroll
+    for (int q = 0; q < VC; ++q) { a[c * VC + q] = t[q]; rm = fmax(rm, fabs(t[q])); }
+  }
+  const T tau = (sizeof(T) == 4) ? T(1e-4) : T(1e-8);
+  bool bad = false;
+  T myr = 0;
+  T piv = __shfl_sync(FULL, a[0], 0);
+  T rs = __shfl_sync(FULL, rm, 0);
+  T r = fast_rcp(piv);
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    if (!(fabs(piv) >= tau * rs && fabs(piv) > T(0))) {
+      // cheap test failed (rare, warp-uniform): the natural row is still acceptable if its pivot is
+      // within tau of the largest candidate of its column inside the block (threshold pivoting)
+      T cand = (lane > k && lane < NB) ? fabs(a[k]) : T(0);
+      if (cand != cand) cand = INFINITY;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cand = fmax(cand, __shfl_xor_sync(FULL, cand, o));
+      bad |= !(fabs(piv) >= tau * cand && fabs(piv) > T(0));
+    }
+    if (lane == k) myr = r;
+    const bool below = lane > k && lane < NB;
+    const T l = a[k] * r;
+    if (below) a[k] = l;
+    if (k + 1 < NB) {
+      // first column of the update, then start the next pivot while the rest is still in flight
+      const T uk1 = __shfl_sync(FULL, a[k + 1], k);
+      if (below) a[k + 1] = fma(-l, uk1, a[k + 1]);
+      piv = __shfl_sync(FULL, a[k + 1], k + 1);
+      rs = __shfl_sync(FULL, rm, k + 1);
+      r = fast_rcp(piv);
+#pragma unroll
+      for (int j = k + 2; j < NB; ++j) {
+        const T ukj = __shfl_sync(FULL, a[j], k);
+        if (below) a[j] = fma(-l, ukj, a[j]);
+      }
+    }
+  }
+  if (bad) return false;
+  if (lane < NB) {
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      T t[VC];
+#pragma unroll
+      for (int q = 0; q < VC; ++q) t[q] = a[c * VC + q];
+      *reinterpret_cast<V*>(row + c * VC) = vec_make(t);
+    }
+    smem_int(o_perm_i)[lane] = lane;
+    (smem_base<T>() + o_rdiag)[lane] = myr;
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Diagonal block (ONE warp -- the critical path of the factorisation): P_b L U of the NB x NB block
+// with rows in REGISTERS and a ROLLED pivot loop. After eliminating a column every live row shifts
+// its registers left by one as part of the FMA that updates them (a[j-1] = a[j] - l u[j]), so the
+// current column is always a[0]: no dynamic register index, no unrolled pivot loop. The loop body is
+// ~1.5 KB of code: a single warp running a 22 KB fully unrolled variant spent 25-30k cycles per
+// block waiting on instruction fetch (ncu: no_instruction / short_scoreboard), this one ~5k.
+// Pivoting: threshold partial pivoting inside the block -- the natural row is kept unless its pivot
+// is below tau * (initial row scale) AND below tau * (largest candidate of the column in the
+// block); only then rows are interchanged (registers via shuffles, the L part in memory).
+// Measured (DESIGN.md "Pivoting"): eager swaps HURT fp32 trajectory parity, never swapping leaves
+// exact-zero pivots on converged scenes.
+// Outputs: D = L\U in place, rdiag[j] = 1/U[j][j], perm[i] = source row of row i, *flag = moved.
+template <typename T, int MODE, int NB>
+__device__ __noinline__ void diag_lu_rot(MPtr<T, MODE> Db, int ld, int o_perm_i, int o_rdiag, int o_flag_i,
+                                         int o_stage) {
+  using V = typename VecOf<T>::type;
+  constexpr int VC = VecOf<T>::VC, NV = NB / VC, SL = NB + VC;
+  T* const D = Db.get();
+  T* const stage = smem_base<T>() + o_stage;     // 2 x (NB + VC): the pivot row + its scale, double-buffered
+  int* const perm = smem_int(o_perm_i);
+  const int lane = threadIdx.x & 31;
+  const int li = lane < NB ? lane : NB - 1;      // lanes >= NB mirror the last row and never store
+  T* row = D + (size_t)li * ld;
+  T a[NB];
+  T rm = 0;
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    T t[VC];
+    vec_get<T>(*reinterpret_cast<const V*>(row + c * VC), t);
+#pragma unroll
+    for (int q = 0; q < VC; ++q) { a[c * VC + q] = t[q]; rm = fmax(rm, fabs(t[q])); }
+  }
+  if (lane < NB) perm[lane] = lane;
+  const T tau = (sizeof(T) == 4) ? T(1e-4) : T(1e-8);
+  bool moved = false;
+  T myr = 0;
+  T u[NB];
+#pragma unroll 1
+  for (int k = 0; k < NB; ++k) {
+    T* const st = stage + (k & 1) * SL;
+    // the pivot row is broadcast through shared memory (8 vector stores by one lane, 8 broadcast
+    // vector loads by all): a warp-wide SHFL issues once per 4 cycles, 31 of them per step were
+    // the bottleneck of the shuffle variant.
+    if (lane == k) {
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        T t[VC];
+#pragma unroll
+        for (int q = 0; q < VC; ++q) t[q] = a[c * VC + q];
+        *reinterpret_cast<V*>(st + c * VC) = vec_make(t);
+      }
+      st[NB] = rm;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      T t[VC];
+      vec_get<T>(*reinterpret_cast<const V*>(st + c * VC), t);
+#pragma unroll
+      for (int q = 0; q < VC; ++q) u[c * VC + q] = t[q];
+    }
+    T piv = u[0];
+    const T rs = st[NB];
+    if (!(fabs(piv) >= tau * rs && fabs(piv) > T(0))) {          // rare, warp-uniform
+      T best = (lane >= k && lane < NB) ? fabs(a[0]) : T(-1);
+      if (best != best) best = INFINITY;
+      int bi = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const T ov = __shfl_xor_sync(FULL, best, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (bi != k && !(fabs(piv) >= tau * best && fabs(piv) > T(0))) {
+        // interchange rows k and bi: live registers (same shift on both), scale, L part, perm
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const T fk = __shfl_sync(FULL, a[j], k), fb = __shfl_sync(FULL, a[j], bi);
+          if (lane == k) a[j] = fb; else if (lane == bi) a[j] = fk;
+          u[j] = fb;                                               // the new pivot row
+        }
+        {
+          const T fk = __shfl_sync(FULL, rm, k), fb = __shfl_sync(FULL, rm, bi);
+          if (lane == k) rm = fb; else if (lane == bi) rm = fk;
+        }
+        if (lane < k) {
+          const T t0 = D[(size_t)k * ld + lane], t1 = D[(size_t)bi * ld + lane];
+          D[(size_t)k * ld + lane] = t1;
+          D[(size_t)bi * ld + lane] = t0;
+        }
+        if (lane == 0) { const int p0 = perm[k]; perm[k] = perm[bi]; perm[bi] = p0; }
+        moved = true;
+        __syncwarp();
+        piv = u[0];
+      }
+    }
+    const T r = fast_rcp(piv);
+    if (lane == k) myr = r;
+    const bool alive = lane > k && lane < NB;
+    const T l = a[0] * r;
+    if (alive) {
+      D[(size_t)lane * ld + k] = l;                              // multiplier: final entry of L
+#pragma unroll
+      for (int j = 1; j < NB; ++j) a[j - 1] = fma(-l, u[j], a[j]);
+    }
+  }
+  // row i stopped shifting after step i: a[j] = U[i][i + j]
+  if (lane < NB) {
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      if (lane + j < NB) D[(size_t)lane * ld + lane + j] = a[j];
+    (smem_base<T>() + o_rdiag)[lane] = myr;
+  }
+  if (lane == 0) *smem_int(o_flag_i) = moved ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Diagonal block, step 1 (the critical path of the factorisation: ONE warp, lane i owns row i of
+// the NB x NB block D). P_b L U by right-looking elimination with reciprocal pivot scaling (getf2)
+// and THRESHOLD pivoting restricted to the rows of the block: the natural row is kept unless its
+// pivot is below tau * (largest entry the row had when the block was loaded); only then the largest
+// |entry| of the column among the remaining rows is swapped in (rows, scales and perm move
+// together). Measured (DESIGN.md "Pivoting"): eager swaps inside a block HURT fp32 trajectory
+// parity, never swapping leaves exact-zero pivots (0/0 -> NaN) on converged scenes.
+// Per pivot every lane loads its row and the pivot row with all vector loads in flight at once,
+// updates, stores (~100 cycles); run-time k loop, so the code is small -- the fully unrolled
+// register/shuffle version was 20x slower (instruction-fetch and shuffle stalls, ncu).
+// Outputs: D = L\U in place, rdiag[j] = 1/U[j][j], perm[i] = source row of row i, *flag = moved.
+template <typename T, int MODE, int NB>
+__device__ __noinline__ void diag_lu_warp(MPtr<T, MODE> Db, int ld, int o_perm_i, int o_rmaxs, int o_rdiag,
+                                          int o_flag_i) {
+  using V = typename VecOf<T>::type;
+  constexpr int VC = VecOf<T>::VC, NV = NB / VC;
+  T* const D = Db.get();
+  int* const perm = smem_int(o_perm_i);
+  T* const rmaxs = smem_base<T>() + o_rmaxs;
+  T* const rdiag = smem_base<T>() + o_rdiag;
   const int lane = threadIdx.x & 31;
   const bool act = lane < NB;
   T* row = D + (size_t)(act ? lane : 0) * ld;
   const T tau = (sizeof(T) == 4) ? T(1e-4) : T(1e-8);
   {
     T rm = 0;
-    for (int j0 = 0; j0 < NB; j0 += VC) {
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
       T a[VC];
-      vec_get<T>(*reinterpret_cast<const V*>(row + j0), a);
+      vec_get<T>(*reinterpret_cast<const V*>(row + c * VC), a);
 #pragma unroll
       for (int q = 0; q < VC; ++q) rm = fmax(rm, fabs(a[q]));
     }
@@ -178,8 +407,10 @@ __device__ __forceinline__ bool diag_block_inplace(T* D, int ld, int* perm, T* r
   }
   __syncwarp();
   bool moved = false;
+#pragma unroll 1
   for (int k = 0; k < NB; ++k) {
-    T piv = D[(size_t)k * ld + k];
+    const T* prow = D + (size_t)k * ld;
+    T piv = prow[k];
     const T rs = rmaxs[k];
     if (!(fabs(piv) >= tau * rs && fabs(piv) > T(0))) {          // rare: partial pivoting inside the block
       T best = (act && lane >= k) ? fabs(row[k]) : T(-1);
@@ -191,7 +422,7 @@ __device__ __forceinline__ bool diag_block_inplace(T* D, int ld, int* perm, T* r
         const int oi = __shfl_xor_sync(FULL, bi, o);
         if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
       }
-      if (bi != k) {
+      if (bi != k && !(fabs(piv) >= tau * best && fabs(piv) > T(0))) {
         if (act) {
           const T t0 = D[(size_t)k * ld + lane], t1 = D[(size_t)bi * ld + lane];
           D[(size_t)k * ld + lane] = t1;
@@ -203,248 +434,441 @@ __device__ __forceinline__ bool diag_block_inplace(T* D, int ld, int* perm, T* r
         }
         moved = true;
         __syncwarp();
-        piv = D[(size_t)k * ld + k];
+        piv = prow[k];
       }
     }
     const T r = T(1) / piv;
+    if (lane == k) rdiag[k] = r;
     if (act && lane > k) {
-      const T l = row[k] * r;
-      const T* prow = D + (size_t)k * ld;
-      for (int j0 = (k / VC) * VC; j0 < NB; j0 += VC) {
-        T u[VC], a[VC];
-        vec_get<T>(*reinterpret_cast<const V*>(prow + j0), u);
-        vec_get<T>(*reinterpret_cast<const V*>(row + j0), a);
+      const int c0 = k / VC;                                     // first chunk that holds a column >= k
+      // all chunks are loaded unconditionally: a conditionally written register array would be
+      // demoted to local memory, and with L1 squeezed to a few KB that is an L2 round trip per access
+      V uv[NV], av[NV];
 #pragma unroll
-        for (int q = 0; q < VC; ++q) {
-          if (j0 + q > k) a[q] = fma(-l, u[q], a[q]);
-          else if (j0 + q == k) a[q] = l;
+      for (int c = 0; c < NV; ++c) { uv[c] = *reinterpret_cast<const V*>(prow + c * VC); av[c] = *reinterpret_cast<const V*>(row + c * VC); }
+      const T l = row[k] * r;
+      // chunks right of the one holding column k: plain FMAs (independent, no selects); the
+      // boundary chunk: per-element select; chunks left of it: untouched
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        if (c > c0) {
+          T u[VC], a[VC];
+          vec_get<T>(uv[c], u);
+          vec_get<T>(av[c], a);
+#pragma unroll
+          for (int q = 0; q < VC; ++q) a[q] = fma(-l, u[q], a[q]);
+          *reinterpret_cast<V*>(row + c * VC) = vec_make(a);
+        } else if (c == c0) {
+          T u[VC], a[VC];
+          vec_get<T>(uv[c], u);
+          vec_get<T>(av[c], a);
+          const int kq = k - c * VC;
+#pragma unroll
+          for (int q = 0; q < VC; ++q) a[q] = (q > kq) ? fma(-l, u[q], a[q]) : ((q == kq) ? l : a[q]);
+          *reinterpret_cast<V*>(row + c * VC) = vec_make(a);
         }
-        *reinterpret_cast<V*>(row + j0) = vec_make(a);
       }
     }
     __syncwarp();
   }
-  // ---- inverses, in place
-  for (int k = 0; k < NB; ++k) {
-    const int kk = NB - 1 - k;
-    if (act && lane > k) {                       // inv(L): rows below k
-      const T mlt = row[k];
-      const T* prow = D + (size_t)k * ld;
-      for (int j0 = 0; j0 <= k; j0 += VC) {
-        T x[VC], a[VC];
-        vec_get<T>(*reinterpret_cast<const V*>(prow + j0), x);
-        vec_get<T>(*reinterpret_cast<const V*>(row + j0), a);
+  if (lane == 0) *smem_int(o_flag_i) = moved ? 1 : 0;
+}
+
+// Diagonal blocks, inverses (run after the whole factorisation, one warp per triangle, all blocks
+// in parallel): D <- [strict-lower(inv L) \ upper(inv U)] IN PLACE, by right-looking substitution.
+// The lower job only ever writes columns < lane of row `lane`, the upper job columns >= lane; the
+// 16-byte chunk that holds the diagonal is shared between them and is accessed element-wise.
+template <typename T, int MODE, int NB>
+__device__ __noinline__ void diag_inverse_lower_inplace(MPtr<T, MODE> Db, int ld) {
+  using V = typename VecOf<T>::type;
+  constexpr int VC = VecOf<T>::VC, NV = NB / VC;
+  T* const D = Db.get();
+  const int lane = threadIdx.x & 31;
+  const bool act = lane < NB;
+  T* row = D + (size_t)(act ? lane : 0) * ld;
+  const int ci = lane / VC;                      // chunk of the own diagonal
+#pragma unroll 1
+  for (int k = 0; k < NB - 1; ++k) {
+    if (act && lane > k) {                       // rows below k, columns <= k
+      const T* xk = D + (size_t)k * ld;          // row k of inv(L) (final): columns < k
+      const int cl = k / VC;
+      const T ml = row[k];
+      V xv[NV], av[NV];
 #pragma unroll
-        for (int q = 0; q < VC; ++q) {
-          if (j0 + q < k) a[q] = fma(-mlt, x[q], a[q]);
-          else if (j0 + q == k) a[q] = -mlt;
+      for (int c = 0; c < NV; ++c) { xv[c] = *reinterpret_cast<const V*>(xk + c * VC); av[c] = *reinterpret_cast<const V*>(row + c * VC); }
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        if (c > cl) continue;
+        T a[VC], x[VC];
+        vec_get<T>(av[c], a);
+        vec_get<T>(xv[c], x);
+        const int kq = k - c * VC;               // >= VC for chunks left of the boundary chunk
+#pragma unroll
+        for (int q = 0; q < VC; ++q) a[q] = (q < kq) ? fma(-ml, x[q], a[q]) : ((q == kq) ? -ml : a[q]);
+        if (c != ci) {
+          *reinterpret_cast<V*>(row + c * VC) = vec_make(a);
+        } else {
+#pragma unroll
+          for (int q = 0; q < VC; ++q)
+            if (q <= kq) row[c * VC + q] = a[q];
         }
-        *reinterpret_cast<V*>(row + j0) = vec_make(a);
       }
     }
-    if (act && lane < kk) {                      // inv(U) (unscaled rows Z): rows above kk
-      const T* prow = D + (size_t)kk * ld;
-      const T f = row[kk] * (T(1) / prow[kk]);
-      for (int j0 = (kk / VC) * VC; j0 < NB; j0 += VC) {
-        T z[VC], a[VC];
-        vec_get<T>(*reinterpret_cast<const V*>(prow + j0), z);
-        vec_get<T>(*reinterpret_cast<const V*>(row + j0), a);
+    __syncwarp();
+  }
+}
+
+template <typename T, int MODE, int NB>
+__device__ __noinline__ void diag_inverse_upper_inplace(MPtr<T, MODE> Db, int ld, int o_rdiag) {
+  using V = typename VecOf<T>::type;
+  constexpr int VC = VecOf<T>::VC, NV = NB / VC;
+  T* const D = Db.get();
+  const T* const rdiag = smem_base<T>() + o_rdiag;
+  const int lane = threadIdx.x & 31;
+  const bool act = lane < NB;
+  T* row = D + (size_t)(act ? lane : 0) * ld;
+  const int ci = lane / VC;
+#pragma unroll 1
+  for (int kk = NB - 1; kk > 0; --kk) {
+    if (act && lane < kk) {                      // unscaled rows Z: rows above kk, columns >= kk
+      const T* zk = D + (size_t)kk * ld;         // row kk of Z (final): columns > kk
+      const int cu = kk / VC;
+      const T fu = row[kk] * rdiag[kk];
+      V zv[NV], av[NV];
 #pragma unroll
-        for (int q = 0; q < VC; ++q) {
-          if (j0 + q > kk) a[q] = fma(-f, z[q], a[q]);
-          else if (j0 + q == kk) a[q] = -f;
+      for (int c = 0; c < NV; ++c) { zv[c] = *reinterpret_cast<const V*>(zk + c * VC); av[c] = *reinterpret_cast<const V*>(row + c * VC); }
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        if (c < cu) continue;
+        T a[VC], z[VC];
+        vec_get<T>(av[c], a);
+        vec_get<T>(zv[c], z);
+        const int kq = kk - c * VC;              // < 0 for chunks right of the boundary chunk
+#pragma unroll
+        for (int q = 0; q < VC; ++q) a[q] = (q > kq) ? fma(-fu, z[q], a[q]) : ((q == kq) ? -fu : a[q]);
+        if (c != ci) {
+          *reinterpret_cast<V*>(row + c * VC) = vec_make(a);
+        } else {
+#pragma unroll
+          for (int q = 0; q < VC; ++q)
+            if (q >= kq) row[c * VC + q] = a[q];
         }
-        *reinterpret_cast<V*>(row + j0) = vec_make(a);
       }
     }
     __syncwarp();
   }
   if (act) {                                     // inv(U)[i][j] = Z[i][j] / U[i][i], inv(U)[i][i] = 1 / U[i][i]
-    const T ri = T(1) / row[lane];
-    for (int j0 = (lane / VC) * VC; j0 < NB; j0 += VC) {
-      T a[VC];
-      vec_get<T>(*reinterpret_cast<const V*>(row + j0), a);
+    const T ri = rdiag[lane];
 #pragma unroll
-      for (int q = 0; q < VC; ++q) {
-        if (j0 + q > lane) a[q] *= ri;
-        else if (j0 + q == lane) a[q] = ri;
+    for (int c = 0; c < NV; ++c) {
+      if (c < ci) continue;
+      if (c != ci) {
+        T a[VC];
+        vec_get<T>(*reinterpret_cast<const V*>(row + c * VC), a);
+#pragma unroll
+        for (int q = 0; q < VC; ++q) a[q] *= ri;
+        *reinterpret_cast<V*>(row + c * VC) = vec_make(a);
+      } else {
+#pragma unroll
+        for (int q = 0; q < VC; ++q) {
+          const int j = c * VC + q;
+          if (j > lane) row[j] *= ri;
+          else if (j == lane) row[j] = ri;
+        }
       }
-      *reinterpret_cast<V*>(row + j0) = vec_make(a);
     }
   }
-  return moved;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Panel solves of one block step. D = diagonal block (already [inv L \ inv U], lcp_device.cuh).
-//   U12 columns  [c_lo, c_hi) of main rows k0..k0+NB:   U12 = inv(L11) A12   (one column per thread)
-//   L21 rows     [r_lo, r_hi):                           L21 = A21 inv(U11)   (one row per thread)
-template <typename T, typename RowFn>
-__device__ __forceinline__ void panel_solves(RowFn rowp, T* Umain, int ldu, int k0, int r_lo, int r_hi, int c_lo,
-                                             int c_hi) {
+// Panel solves of one block step by SUBSTITUTION with the L\U diagonal block (in place, one
+// register array per thread):
+//   panel_cols: U12 columns [c_lo, c_hi) of rows k0..k0+NB of `Ub`:  U12 = L11^{-1} A12  (one column
+//       per thread, left-looking: rows of L11 are read as broadcast vectors)
+//   panel_rows: L21 rows [r_lo, r_hi) of `Cb`:  L21 = A21 U11^{-1}  (one row per thread, right-looking:
+//       rows of U11 are read as broadcast vectors, rdiag = 1/diag(U11))
+// Warps 1..skip_warp do not take part (they are inverting the diagonal block).
+template <typename T, int MODE>
+__device__ __noinline__ void panel_cols(MPtr<T, MODE> Ub, int ldu, int k0, int c_lo, int c_hi, int skip_warp) {
   using V = typename VecOf<T>::type;
   constexpr int VC = VecOf<T>::VC, NB = Blk<T>::NB;
-  const T* D = Umain + (size_t)k0 * ldu + k0;
-  const int ncol = max(c_hi - c_lo, 0), nrow = max(r_hi - r_lo, 0);
-  for (int t = threadIdx.x; t < ncol + nrow; t += blockDim.x) {
-    T a[NB], y[NB];
-    if (t < ncol) {
-      T* col = Umain + (size_t)k0 * ldu + c_lo + t;
+  T* const U = Ub.get();
+  const T* D = U + (size_t)k0 * ldu + k0;
+  const int warp = threadIdx.x >> 5;
+  if (warp >= 1 && warp <= skip_warp) return;                  // warps 1..skip_warp are busy elsewhere
+  const int nthr = blockDim.x - 32 * skip_warp;
+  const int tix = threadIdx.x - (warp > skip_warp ? 32 * skip_warp : 0);
+  for (int t = c_lo + tix; t < c_hi; t += nthr) {
+    T a[NB];
+    T* col = U + (size_t)k0 * ldu + t;
 #pragma unroll
-      for (int r = 0; r < NB; ++r) a[r] = col[(size_t)r * ldu];
+    for (int r = 0; r < NB; ++r) a[r] = col[(size_t)r * ldu];
 #pragma unroll
-      for (int r = 0; r < NB; ++r) {
-        T acc = a[r];
-        // inv(L11)[r][0..r): vector loads along the row (broadcast across the warp)
+    for (int r = 1; r < NB; ++r) {
+      T acc = a[r];
 #pragma unroll
-        for (int q0 = 0; q0 < r; q0 += VC) {
-          T lv[VC];
-          vec_get<T>(*reinterpret_cast<const V*>(D + (size_t)r * ldu + q0), lv);
+      for (int q0 = 0; q0 < r; q0 += VC) {
+        T lv[VC];
+        vec_get<T>(*reinterpret_cast<const V*>(D + (size_t)r * ldu + q0), lv);
 #pragma unroll
-          for (int q = 0; q < VC; ++q)
-            if (q0 + q < r) acc = fma(lv[q], a[q0 + q], acc);
-        }
-        y[r] = acc;
+        for (int q = 0; q < VC; ++q)
+          if (q0 + q < r) acc = fma(-lv[q], a[q0 + q], acc);
       }
+      a[r] = acc;
+    }
 #pragma unroll
-      for (int r = 0; r < NB; ++r) col[(size_t)r * ldu] = y[r];
-    } else {
-      T* row = rowp(r_lo + t - ncol) + k0;
+    for (int r = 1; r < NB; ++r) col[(size_t)r * ldu] = a[r];
+  }
+}
+
+template <typename T, int CMODE, int UMODE>
+__device__ __noinline__ void panel_rows(MPtr<T, CMODE> Cb, int ldc, MPtr<T, UMODE> Ub, int ldu, int k0, int r_lo,
+                                        int r_hi, int o_rdiag, int skip_warp, int tshift) {
+  using V = typename VecOf<T>::type;
+  constexpr int VC = VecOf<T>::VC, NB = Blk<T>::NB;
+  T* const C = Cb.get();
+  const T* D = Ub.get() + (size_t)k0 * ldu + k0;
+  const T* const rdiag = smem_base<T>() + o_rdiag;
+  const int warp = threadIdx.x >> 5;
+  if ((warp >= 1 && warp <= skip_warp) || r_hi <= r_lo) return;
+  const int nthr = blockDim.x - 32 * skip_warp;
+  // rotate the thread ids so that row tasks land on the threads the column tasks left idle
+  int tix = threadIdx.x - (warp > skip_warp ? 32 * skip_warp : 0) - (tshift % nthr);
+  if (tix < 0) tix += nthr;
+  for (int t = r_lo + tix; t < r_hi; t += nthr) {
+    T a[NB];
+    T* row = C + (size_t)t * ldc + k0;
 #pragma unroll
-      for (int c0 = 0; c0 < NB; c0 += VC) {
-        T tv[VC];
-        vec_get<T>(*reinterpret_cast<const V*>(row + c0), tv);
+    for (int c0 = 0; c0 < NB; c0 += VC) {
+      T tv[VC];
+      vec_get<T>(*reinterpret_cast<const V*>(row + c0), tv);
 #pragma unroll
-        for (int q = 0; q < VC; ++q) { a[c0 + q] = tv[q]; y[c0 + q] = 0; }
+      for (int q = 0; q < VC; ++q) a[c0 + q] = tv[q];
+    }
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+      a[r] *= rdiag[r];
+#pragma unroll
+      for (int c0 = (r / VC) * VC; c0 < NB; c0 += VC) {
+        T uv[VC];
+        vec_get<T>(*reinterpret_cast<const V*>(D + (size_t)r * ldu + c0), uv);
+#pragma unroll
+        for (int q = 0; q < VC; ++q)
+          if (c0 + q > r) a[c0 + q] = fma(-a[r], uv[q], a[c0 + q]);
       }
-      // y[c] = sum_{r<=c} a[r] inv(U11)[r][c]: sweep rows of inv(U11), vector loads along the row
+    }
 #pragma unroll
-      for (int r = 0; r < NB; ++r) {
+    for (int c0 = 0; c0 < NB; c0 += VC) {
+      T tv[VC];
 #pragma unroll
-        for (int c0 = (r / VC) * VC; c0 < NB; c0 += VC) {
-          T uv[VC];
-          vec_get<T>(*reinterpret_cast<const V*>(D + (size_t)r * ldu + c0), uv);
-#pragma unroll
-          for (int q = 0; q < VC; ++q)
-            if (c0 + q >= r) y[c0 + q] = fma(a[r], uv[q], y[c0 + q]);
-        }
-      }
-#pragma unroll
-      for (int c0 = 0; c0 < NB; c0 += VC) {
-        T tv[VC];
-#pragma unroll
-        for (int q = 0; q < VC; ++q) tv[q] = y[c0 + q];
-        *reinterpret_cast<V*>(row + c0) = vec_make(tv);
-      }
+      for (int q = 0; q < VC; ++q) tv[q] = a[c0 + q];
+      *reinterpret_cast<V*>(row + c0) = vec_make(tv);
     }
   }
 }
 
-// Apply the block's row interchanges to the columns outside the diagonal block.
-template <typename T, typename RowFn>
-__device__ __forceinline__ void apply_block_perm(RowFn rowp, int k0, const int* perm, int c_begin, int c_end) {
+// Apply the block's row interchanges (rows k0..k0+NB of `Cb`) to columns [c_begin, c_end), except
+// the diagonal block's own columns when skip_diag. Each thread owns one column: no barrier between
+// its reads and writes. perm (region base, int units): perm[k0 + r] = block-local source row.
+template <typename T, int CMODE>
+__device__ __noinline__ void apply_block_perm(MPtr<T, CMODE> Cb, int ldc, int k0, int o_perm_i, int c_begin, int c_end,
+                                              int skip_diag) {
   constexpr int NB = Blk<T>::NB;
-  // each thread owns one column: no barrier between its reads and writes
-  for (int c = c_begin + threadIdx.x; c < c_end - NB; c += blockDim.x) {
-    const int col = c < k0 ? c : c + NB;
+  T* const C = Cb.get();
+  const int* const perm = smem_int(o_perm_i);
+  for (int col = c_begin + threadIdx.x; col < c_end; col += blockDim.x) {
+    if (skip_diag && col >= k0 && col < k0 + NB) continue;
     T tmp[NB];
 #pragma unroll
-    for (int r = 0; r < NB; ++r) tmp[r] = rowp(k0 + perm[k0 + r])[col];
+    for (int r = 0; r < NB; ++r) tmp[r] = C[(size_t)(k0 + perm[k0 + r]) * ldc + col];
 #pragma unroll
-    for (int r = 0; r < NB; ++r) rowp(k0 + r)[col] = tmp[r];
+    for (int r = 0; r < NB; ++r) C[(size_t)(k0 + r) * ldc + col] = tmp[r];
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Factor one square region held entirely in `main`-style storage: rows/cols [0, sz) of the matrix
-// whose (0,0) is at A (ld), optionally with extra "low" rows [sz, sz+nlow) that only carry the L
-// panel (columns [0, sz)) -- the split case's phase 1. perm/flag: shared.
-// shadow (may be null): rows [0,sz) x [0,shadow_cols) of another array that must follow the row
-// interchanges (the L21 rows of the split's second half).
-template <typename T>
-__device__ __forceinline__ void lu_region(T* A, int ld, int sz, int ncols_total, T* low, int ldl, int nlow, int* perm,
-                                          int* flag, T* rmaxs, T* shadow = nullptr, int lds = 0, int shadow_cols = 0) {
+// Factor one square region: rows/cols [0, sz) of the matrix at Ab (ld) with ncols_total columns,
+// optionally with extra "low" rows [sz, sz+nlow) held in Lb (ldl) that only carry the L panel
+// (columns [0, sz)) -- the split case's phase 1. Per block step:
+//   S1  warp 0: L\U of the diagonal block (register fast path, pivoting fallback)        | barrier
+//   S2  everyone: panel solves by substitution                                           | barrier
+//   S3  everyone: trailing update                                                        | barrier
+// The diagonal blocks are left as L\U; their inverses are formed afterwards for all blocks in
+// parallel (lu_invert_diag_blocks). rdiag is indexed by the GLOBAL row (offset o_rdiag + row0).
+// Sb (shadow_cols > 0): rows [0,sz) x [0,shadow_cols) of another shared array that must follow the
+// row interchanges (the L21 rows of the split's second half). row0: global index of this region's
+// first row (perm / rdiag position).
+template <typename T, int MODE>
+__device__ __forceinline__ void lu_region(MPtr<T, MODE> Ab, int ld, int sz, int ncols_total, MPtr<T, 0> Lb, int ldl,
+                                          int nlow, LuVec lv, int row0, long long* prof, MPtr<T, 0> Sb, int ldsh,
+                                          int shadow_cols) {
   constexpr int NB = Blk<T>::NB;
-  auto rowp = [=](int i) -> T* { return i < sz ? A + (size_t)i * ld : low + (size_t)(i - sz) * ldl; };
+  long long t0 = 0;
+  auto lap = [&](int idx) {
+    if (prof && threadIdx.x == 0) { const long long t = clock64(); prof[idx] += t - t0; t0 = t; }
+  };
+  if (prof && threadIdx.x == 0) t0 = clock64();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o_perm_i = lv.o_perm_i + row0;
+  const int o_rdiag = lv.o_rdiag + row0;
+  const int* const flag = smem_int(lv.o_flag_i);
+  // low rows are addressed as rows [sz, sz+nlow) of a re-based array
+  const MPtr<T, 0> Lrb = Lb.plus(-(long long)sz * ldl);
   for (int k0 = 0; k0 < sz; k0 += NB) {
-    if (threadIdx.x < 32) {
-      const bool moved = diag_block_inplace<T, NB>(A + (size_t)k0 * ld + k0, ld, perm + k0, rmaxs);
-      if (threadIdx.x == 0) *flag = moved ? 1 : 0;
+    const MPtr<T, MODE> Db = Ab.plus((long long)k0 * ld + k0);
+    if (warp == 0) {
+      diag_lu_rot<T, MODE, NB>(Db, ld, o_perm_i + k0, o_rdiag + k0, lv.o_flag_i, lv.o_stage);
+      if (prof && lane == 0) { prof[11] += 1; if (*smem_int(lv.o_flag_i)) prof[10] += 1; }
     }
+    lap(6);
     __syncthreads();
+    lap(9);
     if (*flag) {
-      apply_block_perm<T>(rowp, k0, perm, 0, ncols_total);
-      if (shadow) {
-        for (int c = threadIdx.x; c < shadow_cols; c += blockDim.x) {
-          T tmp[NB];
-#pragma unroll
-          for (int r = 0; r < NB; ++r) tmp[r] = shadow[(size_t)(k0 + perm[k0 + r]) * lds + c];
-#pragma unroll
-          for (int r = 0; r < NB; ++r) shadow[(size_t)(k0 + r) * lds + c] = tmp[r];
-        }
-      }
+      apply_block_perm<T, MODE>(Ab, ld, k0, o_perm_i, 0, ncols_total, 1);
+      if (shadow_cols > 0) apply_block_perm<T, 0>(Sb, ldsh, k0, o_perm_i, 0, shadow_cols, 0);
       __syncthreads();
     }
     const int r0 = k0 + NB;
-    if (r0 >= ncols_total && r0 >= sz + nlow) break;
-    panel_solves<T>(rowp, A, ld, k0, r0, sz + nlow, r0, ncols_total);
+    panel_cols<T, MODE>(Ab, ld, k0, r0, ncols_total, 0);
+    panel_rows<T, MODE, MODE>(Ab, ld, Ab, ld, k0, r0, sz, o_rdiag + k0, 0, max(ncols_total - r0, 0));
+    if (nlow > 0)
+      panel_rows<T, 0, MODE>(Lrb, ldl, Ab, ld, k0, sz, sz + nlow, o_rdiag + k0, 0,
+                             max(ncols_total - r0, 0) + max(sz - r0, 0));
     __syncthreads();
+    lap(7);
     // trailing update: rows [r0, sz) x cols [r0, ncols_total)  and  low rows [sz, sz+nlow) x cols [r0, sz)
-    rank_nb_update_auto<T>(rowp, A, ld, k0, r0, sz, r0, ncols_total);
-    if (nlow > 0) rank_nb_update_auto<T>(rowp, A, ld, k0, sz, sz + nlow, r0, sz);
+    rank_nb_update_auto<T, MODE, MODE>(Ab, ld, Ab, ld, k0, r0, sz, r0, ncols_total);
+    if (nlow > 0) rank_nb_update_auto<T, 0, MODE>(Lrb, ldl, Ab, ld, k0, sz, sz + nlow, r0, sz);
+    __syncthreads();
+    lap(8);
+  }
+}
+
+// Diagonal-block inverses: one warp per triangle, lane j owns COLUMN j of the result and runs the
+// whole substitution for it in registers (L x_j = e_j / U x_j = e_j); the L\U entries are read as
+// broadcast vector loads -- no shuffles, no cross-lane dependence. Called by ALL warps of the CTA
+// (a warp without a job passes active = false): a CTA barrier separates every job's reads of the
+// block from the in-place stores.
+//   lower: X = inv(L) (unit diagonal implicit, strict lower part stored);
+//   upper: X = inv(U) (rdiag = 1/diag(U)).
+template <typename T, int MODE, int NB>
+__device__ __noinline__ void diag_inverse_job(MPtr<T, MODE> Db, int ld, int o_rdiag, bool upper, bool active) {
+  using V = typename VecOf<T>::type;
+  constexpr int VC = VecOf<T>::VC;
+  T* const D = Db.get();
+  const T* const rdiag = smem_base<T>() + o_rdiag;
+  const int lane = threadIdx.x & 31;
+  const int lj = lane < NB ? lane : NB - 1;
+  T x[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) x[j] = 0;
+  if (active) {
+    if (!upper) {
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        T acc0 = (i == lj) ? T(1) : T(0), acc1 = 0;
+#pragma unroll
+        for (int q0 = 0; q0 < i; q0 += VC) {
+          T l[VC];
+          vec_get<T>(*reinterpret_cast<const V*>(D + (size_t)i * ld + q0), l);
+#pragma unroll
+          for (int q = 0; q < VC; ++q)
+            if (q0 + q < i) { if (q & 1) acc1 = fma(-l[q], x[q0 + q], acc1); else acc0 = fma(-l[q], x[q0 + q], acc0); }
+        }
+        x[i] = acc0 + acc1;
+      }
+    } else {
+#pragma unroll
+      for (int i = NB - 1; i >= 0; --i) {
+        T acc0 = (i == lj) ? T(1) : T(0), acc1 = 0;
+#pragma unroll
+        for (int q0 = (i / VC) * VC; q0 < NB; q0 += VC) {
+          T uu[VC];
+          vec_get<T>(*reinterpret_cast<const V*>(D + (size_t)i * ld + q0), uu);
+#pragma unroll
+          for (int q = 0; q < VC; ++q)
+            if (q0 + q > i) { if (q & 1) acc1 = fma(-uu[q], x[q0 + q], acc1); else acc0 = fma(-uu[q], x[q0 + q], acc0); }
+        }
+        x[i] = (acc0 + acc1) * rdiag[i];
+      }
+    }
+  }
+  __syncthreads();                               // every job has read its block
+  if (active && lane < NB) {
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+      if (upper ? (i <= lane) : (i > lane)) D[(size_t)i * ld + lane] = x[i];
+  }
+}
+
+// All diagonal blocks of the factored view, both triangles, one warp per job.
+template <typename T, int MODE>
+__device__ __forceinline__ void lu_invert_diag_blocks(const TView<T, MODE>& v, int o_rdiag) {
+  constexpr int NB = Blk<T>::NB;
+  const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int nblk = v.mp / NB, njobs = 2 * nblk;
+  for (int j0 = 0; j0 < njobs; j0 += nw) {
+    const int job = j0 + warp;
+    const bool active = job < njobs;
+    const int b = active ? job >> 1 : 0, k0 = b * NB;
+    // logical block (k0,k0): rows/cols < m1 in main at (k0,k0); the rest at (k0-m1, k0) (S22 region)
+    const MPtr<T, MODE> Db = v.main_.plus(k0 < v.m1 ? (long long)k0 * v.ld + k0 : (long long)(k0 - v.m1) * v.ld + k0);
+    diag_inverse_job<T, MODE, NB>(Db, v.ld, o_rdiag + k0, (job & 1) != 0, active);
     __syncthreads();
   }
 }
 
 // Schur block of the split: S22 = T22 - L21 U12, accumulated in registers (K = m1), T22 = R22 + diag
-// read from the L2 copy `R` (ld = ldr, already offset to (m1,m1)); U12 is spilled to v.u12 and S22
-// written over it in main[0..n2) x [m1, mp).
+// read from the L2 copy `R22` (ld = ldr, already offset to (m1,m1)); U12 is spilled to v.u12 and S22
+// written over it in main[0..n2) x [m1, mp). o_dinv: shared vector 1/d (padded with ones).
 template <typename T, int MODE>
-__device__ __forceinline__ void split_schur(const TView<T, MODE>& v, const T* __restrict__ R22, int ldr,
-                                            const T* dinv, int m_real) {
+__device__ __noinline__ void split_schur(TView<T, MODE> v, const T* __restrict__ R22, int ldr, int o_dinv, int m_real) {
   using V = typename VecOf<T>::type;
   constexpr int VC = VecOf<T>::VC;
   constexpr int TR = 4, WR = 4 * TR, WC = 16 * VC;
   const int m1 = v.m1, n2 = v.mp - v.m1;
   T* const vmain = v.main();
   T* const vlow = v.low();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const T* const dinv = smem_base<T>() + o_dinv;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 3, cg = lane & 7;
   const int ntr = (n2 + WR - 1) / WR, ntc = (n2 + WC - 1) / WC;
-  // every warp owns at most MAXT tiles whose accumulators stay in registers across the spill
-  constexpr int MAXT = 1;
-  T acc[MAXT][TR][2 * VC];
-  int nt = 0;
-  for (int wt = warp; wt < ntr * ntc && nt < MAXT; wt += nw, ++nt) {
-    const int tr_ = wt / ntc, tc_ = wt - tr_ * ntc;
-    const int rbase = tr_ * WR + g, c0 = tc_ * WC + VC * cg, c1 = c0 + 8 * VC;
+  // every warp owns at most one tile whose accumulators stay in registers across the spill
+  // (the planner only selects the split when ntr * ntc <= number of warps)
+  T acc[TR][2 * VC];
+  const int wt = warp;
+  const bool have = wt < ntr * ntc;
+  const int tr_ = have ? wt / ntc : 0, tc_ = have ? wt - tr_ * ntc : 0;
+  const int rbase = tr_ * WR + g, c0 = tc_ * WC + VC * cg, c1 = c0 + 8 * VC;
 #pragma unroll
-    for (int r = 0; r < TR; ++r)
+  for (int r = 0; r < TR; ++r)
 #pragma unroll
-      for (int c = 0; c < 2 * VC; ++c) acc[nt][r][c] = 0;
+    for (int c = 0; c < 2 * VC; ++c) acc[r][c] = 0;
+  if (have) {
     const T* lp[TR];
 #pragma unroll
     for (int r = 0; r < TR; ++r) lp[r] = vlow + (size_t)min(rbase + 4 * r, n2 - 1) * v.ldl;
 #pragma unroll 2
     for (int kc = 0; kc < m1; kc += VC) {
-      T l[TR][VC], u[VC][2 * VC];
+      T l[TR][VC];
 #pragma unroll
       for (int r = 0; r < TR; ++r) vec_get<T>(*reinterpret_cast<const V*>(lp[r] + kc), l[r]);
 #pragma unroll
       for (int kk = 0; kk < VC; ++kk) {
         const T* ur = vmain + (size_t)(kc + kk) * v.ld + m1;
-        T lo[VC], hi[VC];
-        vec_get<T>(*reinterpret_cast<const V*>(ur + min(c0, n2 - VC)), lo);
-        vec_get<T>(*reinterpret_cast<const V*>(ur + min(c1, n2 - VC)), hi);
+        T u[2 * VC];
+        {
+          T lo[VC], hi[VC];
+          vec_get<T>(*reinterpret_cast<const V*>(ur + min(c0, n2 - VC)), lo);
+          vec_get<T>(*reinterpret_cast<const V*>(ur + min(c1, n2 - VC)), hi);
 #pragma unroll
-        for (int q = 0; q < VC; ++q) { u[kk][q] = lo[q]; u[kk][VC + q] = hi[q]; }
+          for (int q = 0; q < VC; ++q) { u[q] = lo[q]; u[VC + q] = hi[q]; }
+        }
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+#pragma unroll
+          for (int c = 0; c < 2 * VC; ++c) acc[r][c] = fma(l[r][kk], u[c], acc[r][c]);
       }
-#pragma unroll
-      for (int r = 0; r < TR; ++r)
-#pragma unroll
-        for (int kk = 0; kk < VC; ++kk)
-#pragma unroll
-          for (int c = 0; c < 2 * VC; ++c) acc[nt][r][c] = fma(l[r][kk], u[kk][c], acc[nt][r][c]);
     }
   }
   __syncthreads();                       // all reads of U12 done
@@ -455,10 +879,7 @@ __device__ __forceinline__ void split_schur(const TView<T, MODE>& v, const T* __
   }
   __syncthreads();
   // S22 = T22 - acc -> main[0..n2) x [m1, mp)
-  nt = 0;
-  for (int wt = warp; wt < ntr * ntc && nt < MAXT; wt += nw, ++nt) {
-    const int tr_ = wt / ntc, tc_ = wt - tr_ * ntc;
-    const int rbase = tr_ * WR + g, c0 = tc_ * WC + VC * cg, c1 = c0 + 8 * VC;
+  if (have) {
 #pragma unroll
     for (int r = 0; r < TR; ++r) {
       const int i = rbase + 4 * r;
@@ -472,8 +893,8 @@ __device__ __forceinline__ void split_schur(const TView<T, MODE>& v, const T* __
         for (int q = 0; q < VC; ++q) {
           const int gi = m1 + i, gj = m1 + c + q;       // global indices in the padded matrix
           T t22 = (gi < m_real && gj < m_real) ? R22[(size_t)i * ldr + c + q] : T(0);
-          if (gi == gj) t22 += (gi < m_real) ? dinv[gi] : T(1);
-          out[q] = t22 - acc[nt][r][hh * VC + q];
+          if (gi == gj) t22 += dinv[gi];
+          out[q] = t22 - acc[r][hh * VC + q];
         }
         *reinterpret_cast<V*>(vmain + (size_t)i * v.ld + m1 + c) = vec_make(out);
       }
@@ -483,36 +904,41 @@ __device__ __forceinline__ void split_schur(const TView<T, MODE>& v, const T* __
 }
 
 // Full factorisation of the view (T must already be loaded: main rows [0,m1) all columns, low rows
-// [m1,mp) columns [0,m1)). R22/ldr/dinv/m_real are only used by the split.
+// [m1,mp) columns [0,m1)). R22/ldr/o_dinv/m_real are only used by the split.
 template <typename T, int MODE>
-__device__ __forceinline__ void lu_factor_view(const TView<T, MODE>& v, const T* R22, int ldr, const T* dinv,
-                                               int m_real, int* perm, int* flag, T* rmaxs) {
+__device__ __forceinline__ void lu_factor_view(const TView<T, MODE>& v, const T* R22, int ldr, int o_dinv, int m_real,
+                                               LuVec lv, long long* prof) {
+  MPtr<T, 0> none; none.off = 0; none.g = nullptr;
   if (MODE != 1) {
-    lu_region<T>(v.main(), v.ld, v.mp, v.mp, (T*)nullptr, 0, 0, perm, flag, rmaxs);
-    return;
+    lu_region<T, MODE>(v.main_, v.ld, v.mp, v.mp, none, 0, 0, lv, 0, prof, none, 0, 0);
+  } else {
+    lu_region<T, MODE>(v.main_, v.ld, v.m1, v.mp, v.low_, v.ldl, v.mp - v.m1, lv, 0, prof, none, 0, 0);
+    split_schur<T, MODE>(v, R22, ldr, o_dinv, m_real);
+    lu_region<T, MODE>(v.main_.plus(v.m1), v.ld, v.mp - v.m1, v.mp - v.m1, none, 0, 0, lv, v.m1, prof, v.low_, v.ldl, v.m1);
   }
-  lu_region<T>(v.main(), v.ld, v.m1, v.mp, v.low(), v.ldl, v.mp - v.m1, perm, flag, rmaxs);
-  split_schur<T, MODE>(v, R22, ldr, dinv, m_real);
-  lu_region<T>(v.main() + v.m1, v.ld, v.mp - v.m1, v.mp - v.m1, (T*)nullptr, 0, 0, perm + v.m1, flag, rmaxs, v.low(),
-               v.ldl, v.m1);
+  long long t0 = (prof && threadIdx.x == 0) ? clock64() : 0;
+  lu_invert_diag_blocks<T, MODE>(v, lv.o_rdiag);
+  if (prof && threadIdx.x == 0) prof[9] += clock64() - t0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// x[mp] (shared) <- T^{-1} x using the factors above. tmp: mp scratch (shared).
+// x[mp] (shared, element offset o_x) <- T^{-1} x using the factors above. o_tmp: mp scratch elements.
 template <typename T, int MODE>
-__device__ __forceinline__ void lu_solve_view(const TView<T, MODE>& v, const int* perm, T* x, T* tmp) {
+__device__ __noinline__ void lu_solve_view(TView<T, MODE> v, int o_perm_i, int o_x, int o_tmp) {
   using V = typename VecOf<T>::type;
   constexpr int VC = VecOf<T>::VC, NB = Blk<T>::NB;
   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
   const int mp = v.mp, m1 = v.m1, n2 = mp - m1;
   const T* const vmain = v.main();
   const T* const vlow = (MODE == 1) ? v.low() : vmain;
+  const int* const perm = smem_int(o_perm_i);
+  T* const x = smem_base<T>() + o_x;
+  T* const tmp = smem_base<T>() + o_tmp;
   for (int i = tid; i < mp; i += NT) tmp[i] = x[(i / NB) * NB + perm[i]];
   __syncthreads();
   for (int i = tid; i < mp; i += NT) x[i] = tmp[i];
   __syncthreads();
-  // block row pointer helpers: L/U entries of logical row i, columns of logical block k0
-  auto lrow = [&](int i, int k0) -> const T* {      // L part (i > block)
+  auto lrow = [&](int i, int k0) -> const T* {      // L entries of logical row i, block column k0
     if (k0 < m1) return (i < m1 ? vmain + (size_t)i * v.ld : vlow + (size_t)(i - m1) * v.ldl) + k0;
     return vmain + (size_t)(i - m1) * v.ld + k0;   // S22 region: row i-m1, column m1 + (k0-m1)
   };
@@ -526,7 +952,11 @@ __device__ __forceinline__ void lu_solve_view(const TView<T, MODE>& v, const int
       if (lane < NB) {
         acc = x[k0 + lane];
         const T* row = dblk(k0) + (size_t)lane * v.ld;
-        for (int q = 0; q < lane; ++q) acc = fma(row[q], x[k0 + q], acc);
+        T a2 = 0;
+        int q = 0;
+        for (; q + 1 < lane; q += 2) { acc = fma(row[q], x[k0 + q], acc); a2 = fma(row[q + 1], x[k0 + q + 1], a2); }
+        if (q < lane) acc = fma(row[q], x[k0 + q], acc);
+        acc += a2;
       }
       __syncwarp();
       if (lane < NB) x[k0 + lane] = acc;
@@ -534,16 +964,18 @@ __device__ __forceinline__ void lu_solve_view(const TView<T, MODE>& v, const int
     __syncthreads();
     for (int i = k0 + NB + tid; i < mp; i += NT) {
       const T* row = lrow(i, k0);
-      T acc = x[i];
+      T acc = x[i], a2 = 0;
 #pragma unroll
-      for (int c0 = 0; c0 < NB; c0 += VC) {
-        T a[VC], y[VC];
+      for (int c0 = 0; c0 < NB; c0 += 2 * VC) {
+        T a[VC], y[VC], b[VC], z[VC];
         vec_get<T>(*reinterpret_cast<const V*>(row + c0), a);
         vec_get<T>(*reinterpret_cast<const V*>(x + k0 + c0), y);
+        vec_get<T>(*reinterpret_cast<const V*>(row + c0 + VC), b);
+        vec_get<T>(*reinterpret_cast<const V*>(x + k0 + c0 + VC), z);
 #pragma unroll
-        for (int q = 0; q < VC; ++q) acc = fma(-a[q], y[q], acc);
+        for (int q = 0; q < VC; ++q) { acc = fma(-a[q], y[q], acc); a2 = fma(-b[q], z[q], a2); }
       }
-      x[i] = acc;
+      x[i] = acc + a2;
     }
     __syncthreads();
   }
@@ -553,43 +985,56 @@ __device__ __forceinline__ void lu_solve_view(const TView<T, MODE>& v, const int
       T acc = 0;
       if (lane < NB) {
         const T* row = dblk(k0) + (size_t)lane * v.ld;
-        for (int c = lane; c < NB; ++c) acc = fma(row[c], x[k0 + c], acc);
+        T a2 = 0;
+        int c = lane;
+        for (; c + 1 < NB; c += 2) { acc = fma(row[c], x[k0 + c], acc); a2 = fma(row[c + 1], x[k0 + c + 1], a2); }
+        if (c < NB) acc = fma(row[c], x[k0 + c], acc);
+        acc += a2;
       }
       __syncwarp();
       if (lane < NB) x[k0 + lane] = acc;
     }
     __syncthreads();
-    // rows above inside the same triangular factor
     const int top = k0 < m1 ? 0 : m1;
     for (int i = top + tid; i < k0; i += NT) {
       const T* row = (k0 < m1 ? vmain + (size_t)i * v.ld : vmain + (size_t)(i - m1) * v.ld) + k0;
-      T acc = x[i];
+      T acc = x[i], a2 = 0;
 #pragma unroll
-      for (int c0 = 0; c0 < NB; c0 += VC) {
-        T a[VC], y[VC];
+      for (int c0 = 0; c0 < NB; c0 += 2 * VC) {
+        T a[VC], y[VC], b[VC], z[VC];
         vec_get<T>(*reinterpret_cast<const V*>(row + c0), a);
         vec_get<T>(*reinterpret_cast<const V*>(x + k0 + c0), y);
+        vec_get<T>(*reinterpret_cast<const V*>(row + c0 + VC), b);
+        vec_get<T>(*reinterpret_cast<const V*>(x + k0 + c0 + VC), z);
 #pragma unroll
-        for (int q = 0; q < VC; ++q) acc = fma(-a[q], y[q], acc);
+        for (int q = 0; q < VC; ++q) { acc = fma(-a[q], y[q], acc); a2 = fma(-b[q], z[q], a2); }
       }
-      x[i] = acc;
+      x[i] = acc + a2;
     }
     __syncthreads();
-    if (k0 == m1 && m1 < mp) {
-      // x1 -= U12 x2, U12 [m1, n2] in L2: one warp per row, coalesced
+    if (MODE == 1 && k0 == m1) {
+      // x1 -= U12 x2, U12 [m1, n2] in L2: one warp per row, 4 rows in flight, coalesced
       const int warp = tid >> 5, nw = NT >> 5;
-      for (int i = warp; i < m1; i += nw) {
-        const T* row = v.u12 + (size_t)i * n2;
-        T acc = 0;
+      for (int i0 = warp * 4; i0 < m1; i0 += nw * 4) {
+        T acc[4] = {0, 0, 0, 0};
         for (int j = lane * VC; j < n2; j += 32 * VC) {
-          T a[VC], y[VC];
-          vec_get<T>(*reinterpret_cast<const V*>(row + j), a);
+          T y[VC];
           vec_get<T>(*reinterpret_cast<const V*>(x + m1 + j), y);
 #pragma unroll
-          for (int q = 0; q < VC; ++q) acc = fma(a[q], y[q], acc);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            T a[VC];
+            vec_get<T>(*reinterpret_cast<const V*>(v.u12 + (size_t)min(i0 + q4, m1 - 1) * n2 + j), a);
+#pragma unroll
+            for (int q = 0; q < VC; ++q) acc[q4] = fma(a[q], y[q], acc[q4]);
+          }
         }
-        acc = warp_reduce(acc, OpSum());
-        if (lane == 0) x[i] -= acc;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) acc[q4] = warp_reduce(acc[q4], OpSum());
+        if (lane == 0) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            if (i0 + q4 < m1) x[i0 + q4] -= acc[q4];
+        }
       }
       __syncthreads();
     }

@@ -21,6 +21,7 @@ struct Plan {
   int mode;                   // 0 smem, 1 split, 2 L2
   int ldT, ldL, ldG, ldQi;
   int stage_ld;               // leading dimension for staging G in T's region during pre-factor (0 = no)
+  int lds;                    // leading dimension of the diagonal-block staging tile
   int G_smem, Qi_smem;
   int off_T, off_L, off_G, off_Qi, off_vec;   // shared offsets, in elements
   int smem_bytes;
@@ -29,7 +30,8 @@ struct Plan {
 };
 
 // phases for the optional cycle counters
-enum { PH_PREFACTOR = 0, PH_LOADT, PH_LU, PH_SOLVE, PH_RESID, PH_STEP, PH_COUNT };
+enum { PH_PREFACTOR = 0, PH_LOADT, PH_LU, PH_SOLVE, PH_RESID, PH_STEP, PH_LU_DIAG, PH_LU_PANEL, PH_LU_UPDATE,
+       PH_LU_DIAGWAIT, PH_LU_SLOWDIAG, PH_LU_BLOCKS, PH_COUNT };
 
 template <typename T>
 struct Vecs {
@@ -43,7 +45,10 @@ struct Vecs {
   T *scratch;                 // max(4 nt, mp) elements
   T *red;                     // 128 elements
   int *perm;                  // mp ints
-  __host__ __device__ long long carve(T* base, int n, int mp, int e, int nt) {
+  T *stage;                   // (unused)
+  T *rdiag;                   // mp reciprocals of the U diagonal
+  int *iflag;                 // 4 ints: [0] = rows were interchanged in the current diagonal block
+  __host__ __device__ long long carve(T* base, int n, int mp, int e, int nt, int nb, int lds) {
     long long o = 0;
 #define LCPB200_TAKE(ptr, cnt) do { ptr = base + o; o += ((cnt) + 3) & ~3; } while (0)
     LCPB200_TAKE(x, n); LCPB200_TAKE(s, mp); LCPB200_TAKE(z, mp); LCPB200_TAKE(y, e); LCPB200_TAKE(d, mp);
@@ -55,6 +60,9 @@ struct Vecs {
     LCPB200_TAKE(rs2, mp);
     LCPB200_TAKE(scratch, 4 * nt > mp ? 4 * nt : mp); LCPB200_TAKE(red, 128);
     { T* pp; LCPB200_TAKE(pp, mp); perm = reinterpret_cast<int*>(pp); }
+    LCPB200_TAKE(stage, 4); LCPB200_TAKE(rdiag, mp);
+    (void)nb; (void)lds;
+    { T* pp; LCPB200_TAKE(pp, 4); iflag = reinterpret_cast<int*>(pp); }
 #undef LCPB200_TAKE
     return o;
   }
@@ -62,7 +70,7 @@ struct Vecs {
 
 template <typename T, int MODE>
 struct SceneCtx {
-  int n, m, e, mp, nt, off_vec;
+  int n, m, e, mp, nt, off_vec, lds;
   const T *Q, *G, *A, *F;     // this scene's inputs (G may point at the shared copy)
   int ldG;
   T *Qi; int ldQi;
@@ -78,7 +86,7 @@ struct SceneCtx {
   // provably shared inside every (non-inlined) device function
   __device__ __forceinline__ Vecs<T> vecs() const {
     Vecs<T> v;
-    v.carve(smem_base<T>() + off_vec, n, mp, e, nt);
+    v.carve(smem_base<T>() + off_vec, n, mp, e, nt, Blk<T>::NB, lds);
     return v;
   }
 };
@@ -329,7 +337,9 @@ __device__ __noinline__ void factor_kkt(SceneCtx<T, MODE>& c) {
       T val[VC];
       if (i < m && j < m) vec_get<T>(*reinterpret_cast<const V*>(c.R + (size_t)i * m + j), val);
       else { for (int q = 0; q < VC; ++q) val[q] = 0; }
-      if (i >= j && i < j + VC) val[i - j] += dinv[i];
+#pragma unroll
+      for (int q = 0; q < VC; ++q)
+        if (j + q == i) val[q] += dinv[i];
       *reinterpret_cast<V*>(tmain + (size_t)i * c.tv.ld + j) = vec_make(val);
     }
     // low rows [m1,mp) x columns [0,m1)
@@ -356,7 +366,14 @@ __device__ __noinline__ void factor_kkt(SceneCtx<T, MODE>& c) {
   }
   __syncthreads();
   prof_lap(c, PH_LOADT);
-  lu_factor_view<T, MODE>(c.tv, c.R + (size_t)m1 * m + m1, m, dinv, m, v.perm, c.lu_flag, v.red);
+  LuVec lv;
+  lv.o_perm_i = (int)(v.perm - smem_int(0));
+  lv.o_flag_i = (int)(v.iflag - smem_int(0));
+  lv.o_rmaxs = (int)(v.red - smem_base<T>());
+  lv.o_rdiag = (int)(v.rdiag - smem_base<T>());
+  lv.o_stage = (int)(v.red - smem_base<T>());   // 2 x (NB + VC) elements of the (idle) reduction buffer
+  lv.lds = c.lds;
+  lu_factor_view<T, MODE>(c.tv, c.R + (size_t)m1 * m + m1, m, (int)(dinv - smem_base<T>()), m, lv, c.prof);
   prof_lap(c, PH_LU);
 }
 
@@ -389,7 +406,7 @@ __device__ __noinline__ void solve_kkt(SceneCtx<T, MODE>& c, int o_rx, int o_rs,
     gemv_rows_v(c.S11, e, e, e, v.hy, [&](int i, T a) { v.te[i] = a; });
     gemv_rows_v(c.Vm, e, m, e, v.te, [&](int i, T a) { v.hz[i] -= a; });
   }
-  lu_solve_view<T, MODE>(c.tv, v.perm, v.hz, v.scratch);               // hz <- T^{-1}(..) = -w_z   (hz[m..mp) stays 0)
+  lu_solve_view<T, MODE>(c.tv, (int)(v.perm - smem_int(0)), (int)(v.hz - smem_base<T>()), (int)(v.scratch - smem_base<T>()));               // hz <- T^{-1}(..) = -w_z   (hz[m..mp) stays 0)
   if (e > 0) gemv_rows_v(c.W, m, e, m, v.hz, [&](int i, T a) { dy[i] = -(v.te[i] - a); });
   for (int i = tid; i < m; i += NT) {
     const T wz = -v.hz[i];
@@ -443,10 +460,10 @@ struct FwdArgs {
 
 template <typename T, int MODE>
 __device__ void setup_ctx(SceneCtx<T, MODE>& c, const Plan& P, T* sm, T* ws, int* lu_flag, long long* prof) {
-  c.n = P.n; c.m = P.m; c.e = P.e; c.mp = P.mp; c.nt = P.nt; c.off_vec = P.off_vec;
+  c.n = P.n; c.m = P.m; c.e = P.e; c.mp = P.mp; c.nt = P.nt; c.off_vec = P.off_vec; c.lds = P.lds;
   c.Qi = P.Qi_smem ? sm + P.off_Qi : ws + P.w_Qi; c.ldQi = P.ldQi;
   c.tv.mp = P.mp; c.tv.m1 = P.m1;
-  c.tv.main_off = P.off_T; c.tv.low_off = P.off_L; c.tv.main_g = ws + P.w_T;
+  c.tv.main_.off = P.off_T; c.tv.main_.g = ws + P.w_T; c.tv.low_.off = P.off_L; c.tv.low_.g = nullptr;
   c.tv.ld = P.ldT; c.tv.ldl = P.ldL;
   c.tv.u12 = ws + P.w_U12;
   c.R = ws + P.w_R; c.X = ws + P.w_X; c.XA = ws + P.w_XA; c.S11 = ws + P.w_S11;

@@ -74,7 +74,8 @@ static int make_plan(lcpb200_handle_s* h) {
   const int mp = P.mp;
   P.nt = (mp >= 96 || n >= 96) ? 512 : (mp >= 64 ? 256 : 128);
   Vecs<T> vv;
-  const long long vec_elems = vv.carve(nullptr, n, mp, e, P.nt);
+  P.lds = pad_ld(NB, w);
+  const long long vec_elems = vv.carve(nullptr, n, mp, e, P.nt, NB, P.lds);
   long long budget = (long long)h->smem_optin - 1024 - vec_elems * w;   // bytes
   if (budget < 0) return fail("problem too large: the shared-memory vectors alone exceed the per-CTA limit");
   auto al4 = [](long long x) { return (x + 3) & ~3LL; };
@@ -297,7 +298,7 @@ extern "C" int lcpb200_backward(lcpb200_handle_t h, int B, const void* Q, const 
 
 extern "C" int lcpb200_profile(lcpb200_handle_t h, int enable, long long* out) {
   // Development aid: per-phase SM cycle counters (thread 0 of every CTA), summed over CTAs.
-  // enable = 1 allocates + zeroes the counters, 0 frees them; `out` (PH_COUNT = 6 values:
+  // enable = 1 allocates + zeroes the counters, 0 frees them; `out` (PH_COUNT = 12 values:
   // prefactor, load T, LU, KKT solves, residuals, step rules) receives the current sums.
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->device));

@@ -29,9 +29,10 @@ def run(name, B, nb, nc, fd, e, dtype, reps=3, bwd=True):
     out = solve_forward(*inp, max_iter=10)
     torch.cuda.synchronize()
     pr = hd.profile(False)
-    tot = sum(pr.values()) or 1
+    tot = sum(v for k, v in pr.items() if not k.startswith('lu_')) or 1
     ncta = min(B, 148)
-    print("  fwd phases (share, kcycles/scene): " + ", ".join("%s %.0f%% %.0fk" % (k, 100.0 * v / tot, v / B / 1e3) for k, v in pr.items()), flush=True)
+    print("  fwd phases (share, kcycles/scene): " + ", ".join("%s %.0f%% %.0fk" % (k, 100.0 * v / tot, v / B / 1e3) for k, v in pr.items() if "blocks" not in k), flush=True)
+    print("  diagonal blocks: %d, pivoting fallback: %d" % (pr["lu_blocks"], pr["lu_slow_blocks"]), flush=True)
     print("  %s B=%d fwd %.2f ms (%.0f solves/s) bwd %.2f ms  fwd+bwd %.0f solves/s  mean iters %.2f" %
           (name, B, tf, B / tf * 1e3, tb, B / (tf + tb) * 1e3, it), flush=True)
 
