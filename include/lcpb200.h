@@ -79,10 +79,12 @@ size_t lcpb200_workspace_bytes(lcpb200_handle_t h);
 int lcpb200_describe(lcpb200_handle_t h, char* buf, size_t len);
 
 /* Development aid: per-phase SM cycle counters of the solver kernels, summed over CTAs.
- * enable=1 allocates/zeroes them, 0 frees; out (may be NULL) receives 12 values:
+ * enable=1 allocates/zeroes them, 0 frees; out (may be NULL) receives 14 values:
  * {prefactor, load T, LU, KKT solves, residuals, step rules,
- *  LU: diagonal blocks, LU: panel solves, LU: trailing updates, LU: diagonal-block inverses,
- *  number of diagonal blocks that needed the pivoting fallback, number of diagonal blocks}. */
+ *  LU: diagonal blocks (look-ahead warp), LU: panel solves, LU: trailing updates,
+ *  LU: diagonal-block inverses, number of diagonal blocks with row interchanges, number of
+ *  diagonal blocks, LU: look-ahead warp's panel pieces + block update, LU: other warps waiting
+ *  for the look-ahead warp}. */
 int lcpb200_profile(lcpb200_handle_t h, int enable, long long* out);
 
 /* LCPFunction.forward. Outputs: zhat[B,n], nu[B,e] (NULL if e==0), lam[B,m],

@@ -72,16 +72,20 @@ struct LuVec {
 // bytes per instruction, broadcast to the 4 row groups) bank-conflict-free for ld = 4 (mod 32) words.
 template <typename T, int CMODE, int UMODE, int TR>
 __device__ __noinline__ void rank_nb_update(MPtr<T, CMODE> Cb, int ldc, MPtr<T, UMODE> Ub, int ldu, int k0, int r_lo,
-                                            int r_hi, int c_lo, int c_hi) {
+                                            int r_hi, int c_lo, int c_hi, int wid, int nwk, int wshift) {
   using V = typename VecOf<T>::type;
   constexpr int VC = VecOf<T>::VC, NB = Blk<T>::NB;
   constexpr int WR = 4 * TR, WC = 16 * VC;
   T* const C = Cb.get();
   const T* const U = Ub.get();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int g = lane >> 3, cg = lane & 7;
   const int ntr = (r_hi - r_lo + WR - 1) / WR, ntc = (c_hi - c_lo + WC - 1) / WC;
-  for (int wt = warp; wt < ntr * ntc; wt += nw) {
+  // tiles are dealt to the nwk participating warps starting at warp (wshift mod nwk), so that
+  // back-to-back calls without a barrier in between continue where the previous one stopped
+  int w0 = wid - wshift % nwk;
+  if (w0 < 0) w0 += nwk;
+  for (int wt = w0; wt < ntr * ntc; wt += nwk) {
     const int tr_ = wt / ntc, tc_ = wt - tr_ * ntc;
     const int rbase = r_lo + tr_ * WR + g;
     const int c0 = c_lo + tc_ * WC + VC * cg, c1 = c0 + 8 * VC;
@@ -140,21 +144,29 @@ __device__ __noinline__ void rank_nb_update(MPtr<T, CMODE> Cb, int ldc, MPtr<T, 
   }
 }
 
-// Pick the thread-tile height so that the warp tiles roughly fill the CTA.
+// Pick the thread-tile height so that the warp tiles roughly fill the participating warps
+// (wid in [0, nwk); a warp with wid < 0 does not take part). Returns the number of tiles dealt,
+// the caller adds it to wshift of its next call.
 template <typename T, int CMODE, int UMODE>
-__device__ __forceinline__ void rank_nb_update_auto(MPtr<T, CMODE> Cb, int ldc, MPtr<T, UMODE> Ub, int ldu, int k0,
-                                                    int r_lo, int r_hi, int c_lo, int c_hi) {
+__device__ __forceinline__ int rank_nb_update_auto(MPtr<T, CMODE> Cb, int ldc, MPtr<T, UMODE> Ub, int ldu, int k0,
+                                                   int r_lo, int r_hi, int c_lo, int c_hi, int wid, int nwk,
+                                                   int wshift) {
   constexpr int VC = VecOf<T>::VC;
-  if (r_hi <= r_lo || c_hi <= c_lo) return;
-  const int nw = blockDim.x >> 5;
+  if (r_hi <= r_lo || c_hi <= c_lo) return 0;
   const int ntc = (c_hi - c_lo + 16 * VC - 1) / (16 * VC);
   const int rows = r_hi - r_lo;
   const int t8 = ((rows + 31) / 32) * ntc, t4 = ((rows + 15) / 16) * ntc, t2 = ((rows + 7) / 8) * ntc;
   // rounds(t) * cost(tile); the constant models the per-tile load/store overhead
-  const int c8 = ((t8 + nw - 1) / nw) * 17, c4 = ((t4 + nw - 1) / nw) * 9, c2 = ((t2 + nw - 1) / nw) * 5;
-  if (c8 <= c4 && c8 <= c2) rank_nb_update<T, CMODE, UMODE, 8>(Cb, ldc, Ub, ldu, k0, r_lo, r_hi, c_lo, c_hi);
-  else if (c4 <= c2) rank_nb_update<T, CMODE, UMODE, 4>(Cb, ldc, Ub, ldu, k0, r_lo, r_hi, c_lo, c_hi);
-  else rank_nb_update<T, CMODE, UMODE, 2>(Cb, ldc, Ub, ldu, k0, r_lo, r_hi, c_lo, c_hi);
+  const int c8 = ((t8 + nwk - 1) / nwk) * 17, c4 = ((t4 + nwk - 1) / nwk) * 9, c2 = ((t2 + nwk - 1) / nwk) * 5;
+  if (c8 <= c4 && c8 <= c2) {
+    if (wid >= 0) rank_nb_update<T, CMODE, UMODE, 8>(Cb, ldc, Ub, ldu, k0, r_lo, r_hi, c_lo, c_hi, wid, nwk, wshift);
+    return t8;
+  } else if (c4 <= c2) {
+    if (wid >= 0) rank_nb_update<T, CMODE, UMODE, 4>(Cb, ldc, Ub, ldu, k0, r_lo, r_hi, c_lo, c_hi, wid, nwk, wshift);
+    return t4;
+  }
+  if (wid >= 0) rank_nb_update<T, CMODE, UMODE, 2>(Cb, ldc, Ub, ldu, k0, r_lo, r_hi, c_lo, c_hi, wid, nwk, wshift);
+  return t2;
 }
 
 // Reciprocal off the slow IEEE-division path: hardware approximation + Newton steps (<= 1 ulp for
@@ -177,82 +189,6 @@ __device__ __forceinline__ double fast_rcp(double x) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Diagonal block, fast path (ONE warp): rows in REGISTERS, pivot rows broadcast by shuffles, fully
-// unrolled: the natural pivot order is taken speculatively and every pivot is checked against the
-// threshold rule (|pivot| >= tau * initial row scale, or else: it is the largest candidate of its
-// column inside the block); if a check fails NOTHING is written back and the caller runs the
-// pivoting routine below on the untouched block. The next
-// pivot's broadcast + reciprocal are issued right after the first column of the update, so their
-// latency hides behind the rest of the update (measured: 290 -> ~100 cycles per pivot).
-// On success: D = L\U in place, rdiag[j] = 1/U[j][j], perm = identity. Returns success (uniform).
-template <typename T, int MODE, int NB>
-__device__ __noinline__ bool diag_lu_regs(MPtr<T, MODE> Db, int ld, int o_perm_i, int o_rdiag) {
-  using V = typename VecOf<T>::type;
-  constexpr int VC = VecOf<T>::VC, NV = NB / VC;
-  T* const D = Db.get();
-  const int lane = threadIdx.x & 31;
-  const int li = lane < NB ? lane : NB - 1;      // lanes >= NB mirror the last row and never store
-  T* row = D + (size_t)li * ld;
-  T a[NB];
-  T rm = 0;
-#pragma unroll
-  for (int c = 0; c < NV; ++c) {
-    T t[VC];
-    vec_get<T>(*reinterpret_cast<const V*>(row + c * VC), t);
-#pragma unroll
-    for (int q = 0; q < VC; ++q) { a[c * VC + q] = t[q]; rm = fmax(rm, fabs(t[q])); }
-  }
-  const T tau = (sizeof(T) == 4) ? T(1e-4) : T(1e-8);
-  bool bad = false;
-  T myr = 0;
-  T piv = __shfl_sync(FULL, a[0], 0);
-  T rs = __shfl_sync(FULL, rm, 0);
-  T r = fast_rcp(piv);
-#pragma unroll
-  for (int k = 0; k < NB; ++k) {
-    if (!(fabs(piv) >= tau * rs && fabs(piv) > T(0))) {
-      // cheap test failed (rare, warp-uniform): the natural row is still acceptable if its pivot is
-      // within tau of the largest candidate of its column inside the block (threshold pivoting)
-      T cand = (lane > k && lane < NB) ? fabs(a[k]) : T(0);
-      if (cand != cand) cand = INFINITY;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) cand = fmax(cand, __shfl_xor_sync(FULL, cand, o));
-      bad |= !(fabs(piv) >= tau * cand && fabs(piv) > T(0));
-    }
-    if (lane == k) myr = r;
-    const bool below = lane > k && lane < NB;
-    const T l = a[k] * r;
-    if (below) a[k] = l;
-    if (k + 1 < NB) {
-      // first column of the update, then start the next pivot while the rest is still in flight
-      const T uk1 = __shfl_sync(FULL, a[k + 1], k);
-      if (below) a[k + 1] = fma(-l, uk1, a[k + 1]);
-      piv = __shfl_sync(FULL, a[k + 1], k + 1);
-      rs = __shfl_sync(FULL, rm, k + 1);
-      r = fast_rcp(piv);
-#pragma unroll
-      for (int j = k + 2; j < NB; ++j) {
-        const T ukj = __shfl_sync(FULL, a[j], k);
-        if (below) a[j] = fma(-l, ukj, a[j]);
-      }
-    }
-  }
-  if (bad) return false;
-  if (lane < NB) {
-#pragma unroll
-    for (int c = 0; c < NV; ++c) {
-      T t[VC];
-#pragma unroll
-      for (int q = 0; q < VC; ++q) t[q] = a[c * VC + q];
-      *reinterpret_cast<V*>(row + c * VC) = vec_make(t);
-    }
-    smem_int(o_perm_i)[lane] = lane;
-    (smem_base<T>() + o_rdiag)[lane] = myr;
-  }
-  return true;
-}
-
-// ---------------------------------------------------------------------------------------------
 // Diagonal block (ONE warp -- the critical path of the factorisation): P_b L U of the NB x NB block
 // with rows in REGISTERS and a ROLLED pivot loop. After eliminating a column every live row shifts
 // its registers left by one as part of the FMA that updates them (a[j-1] = a[j] - l u[j]), so the
@@ -267,7 +203,7 @@ __device__ __noinline__ bool diag_lu_regs(MPtr<T, MODE> Db, int ld, int o_perm_i
 // Outputs: D = L\U in place, rdiag[j] = 1/U[j][j], perm[i] = source row of row i, *flag = moved.
 template <typename T, int MODE, int NB>
 __device__ __noinline__ void diag_lu_rot(MPtr<T, MODE> Db, int ld, int o_perm_i, int o_rdiag, int o_flag_i,
-                                         int o_stage) {
+                                         int o_stage, int fuse_update) {
   using V = typename VecOf<T>::type;
   constexpr int VC = VecOf<T>::VC, NV = NB / VC, SL = NB + VC;
   T* const D = Db.get();
@@ -277,19 +213,41 @@ __device__ __noinline__ void diag_lu_rot(MPtr<T, MODE> Db, int ld, int o_perm_i,
   const int li = lane < NB ? lane : NB - 1;      // lanes >= NB mirror the last row and never store
   T* row = D + (size_t)li * ld;
   T a[NB];
-  T rm = 0;
+  T u[NB];
 #pragma unroll
   for (int c = 0; c < NV; ++c) {
     T t[VC];
     vec_get<T>(*reinterpret_cast<const V*>(row + c * VC), t);
 #pragma unroll
-    for (int q = 0; q < VC; ++q) { a[c * VC + q] = t[q]; rm = fmax(rm, fabs(t[q])); }
+    for (int q = 0; q < VC; ++q) a[c * VC + q] = t[q];
   }
+  if (fuse_update) {
+    // look-ahead: this block still lacks the previous step's rank-NB update,
+    // block -= L21 (same rows, NB columns to the left) * U12 (same columns, NB rows above)
+    const T* lrow = row - NB;
+    const T* ub = D - (size_t)NB * ld;
+#pragma unroll 1
+    for (int p = 0; p < NB; ++p) {
+      const T l = lrow[p];
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        T t[VC];
+        vec_get<T>(*reinterpret_cast<const V*>(ub + (size_t)p * ld + c * VC), t);
+#pragma unroll
+        for (int q = 0; q < VC; ++q) a[c * VC + q] = fma(-l, t[q], a[c * VC + q]);
+      }
+    }
+  }
+  T rm = 0;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) rm = fmax(rm, fabs(a[j]));
   if (lane < NB) perm[lane] = lane;
   const T tau = (sizeof(T) == 4) ? T(1e-4) : T(1e-8);
   bool moved = false;
   T myr = 0;
-  T u[NB];
+  // every lane keeps the reciprocal of its leading entry ready: the pivot lane publishes it with
+  // its row, which takes the reciprocal's latency off the step-to-step dependence chain
+  T rinv = fast_rcp(a[0]);
 #pragma unroll 1
   for (int k = 0; k < NB; ++k) {
     T* const st = stage + (k & 1) * SL;
@@ -305,6 +263,7 @@ __device__ __noinline__ void diag_lu_rot(MPtr<T, MODE> Db, int ld, int o_perm_i,
         *reinterpret_cast<V*>(st + c * VC) = vec_make(t);
       }
       st[NB] = rm;
+      st[NB + 1] = rinv;
     }
     __syncwarp();
 #pragma unroll
@@ -316,6 +275,7 @@ __device__ __noinline__ void diag_lu_rot(MPtr<T, MODE> Db, int ld, int o_perm_i,
     }
     T piv = u[0];
     const T rs = st[NB];
+    T r = st[NB + 1];
     if (!(fabs(piv) >= tau * rs && fabs(piv) > T(0))) {          // rare, warp-uniform
       T best = (lane >= k && lane < NB) ? fabs(a[0]) : T(-1);
       if (best != best) best = INFINITY;
@@ -347,17 +307,17 @@ __device__ __noinline__ void diag_lu_rot(MPtr<T, MODE> Db, int ld, int o_perm_i,
         moved = true;
         __syncwarp();
         piv = u[0];
+        r = fast_rcp(piv);
       }
     }
-    const T r = fast_rcp(piv);
     if (lane == k) myr = r;
     const bool alive = lane > k && lane < NB;
     const T l = a[0] * r;
-    if (alive) {
-      D[(size_t)lane * ld + k] = l;                              // multiplier: final entry of L
+    if (alive) D[(size_t)lane * ld + k] = l;                     // multiplier: final entry of L
 #pragma unroll
-      for (int j = 1; j < NB; ++j) a[j - 1] = fma(-l, u[j], a[j]);
-    }
+    for (int j = 1; j < NB; ++j)
+      if (alive) a[j - 1] = fma(-l, u[j], a[j]);
+    rinv = fast_rcp(a[0]);
   }
   // row i stopped shifting after step i: a[j] = U[i][i + j]
   if (lane < NB) {
@@ -370,234 +330,20 @@ __device__ __noinline__ void diag_lu_rot(MPtr<T, MODE> Db, int ld, int o_perm_i,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Diagonal block, step 1 (the critical path of the factorisation: ONE warp, lane i owns row i of
-// the NB x NB block D). P_b L U by right-looking elimination with reciprocal pivot scaling (getf2)
-// and THRESHOLD pivoting restricted to the rows of the block: the natural row is kept unless its
-// pivot is below tau * (largest entry the row had when the block was loaded); only then the largest
-// |entry| of the column among the remaining rows is swapped in (rows, scales and perm move
-// together). Measured (DESIGN.md "Pivoting"): eager swaps inside a block HURT fp32 trajectory
-// parity, never swapping leaves exact-zero pivots (0/0 -> NaN) on converged scenes.
-// Per pivot every lane loads its row and the pivot row with all vector loads in flight at once,
-// updates, stores (~100 cycles); run-time k loop, so the code is small -- the fully unrolled
-// register/shuffle version was 20x slower (instruction-fetch and shuffle stalls, ncu).
-// Outputs: D = L\U in place, rdiag[j] = 1/U[j][j], perm[i] = source row of row i, *flag = moved.
-template <typename T, int MODE, int NB>
-__device__ __noinline__ void diag_lu_warp(MPtr<T, MODE> Db, int ld, int o_perm_i, int o_rmaxs, int o_rdiag,
-                                          int o_flag_i) {
-  using V = typename VecOf<T>::type;
-  constexpr int VC = VecOf<T>::VC, NV = NB / VC;
-  T* const D = Db.get();
-  int* const perm = smem_int(o_perm_i);
-  T* const rmaxs = smem_base<T>() + o_rmaxs;
-  T* const rdiag = smem_base<T>() + o_rdiag;
-  const int lane = threadIdx.x & 31;
-  const bool act = lane < NB;
-  T* row = D + (size_t)(act ? lane : 0) * ld;
-  const T tau = (sizeof(T) == 4) ? T(1e-4) : T(1e-8);
-  {
-    T rm = 0;
-#pragma unroll
-    for (int c = 0; c < NV; ++c) {
-      T a[VC];
-      vec_get<T>(*reinterpret_cast<const V*>(row + c * VC), a);
-#pragma unroll
-      for (int q = 0; q < VC; ++q) rm = fmax(rm, fabs(a[q]));
-    }
-    if (act) { rmaxs[lane] = rm; perm[lane] = lane; }
-  }
-  __syncwarp();
-  bool moved = false;
-#pragma unroll 1
-  for (int k = 0; k < NB; ++k) {
-    const T* prow = D + (size_t)k * ld;
-    T piv = prow[k];
-    const T rs = rmaxs[k];
-    if (!(fabs(piv) >= tau * rs && fabs(piv) > T(0))) {          // rare: partial pivoting inside the block
-      T best = (act && lane >= k) ? fabs(row[k]) : T(-1);
-      if (best != best) best = INFINITY;
-      int bi = lane;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const T ov = __shfl_xor_sync(FULL, best, o);
-        const int oi = __shfl_xor_sync(FULL, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-      }
-      if (bi != k && !(fabs(piv) >= tau * best && fabs(piv) > T(0))) {
-        if (act) {
-          const T t0 = D[(size_t)k * ld + lane], t1 = D[(size_t)bi * ld + lane];
-          D[(size_t)k * ld + lane] = t1;
-          D[(size_t)bi * ld + lane] = t0;
-        }
-        if (lane == 0) {
-          const T r0 = rmaxs[k]; rmaxs[k] = rmaxs[bi]; rmaxs[bi] = r0;
-          const int p0 = perm[k]; perm[k] = perm[bi]; perm[bi] = p0;
-        }
-        moved = true;
-        __syncwarp();
-        piv = prow[k];
-      }
-    }
-    const T r = T(1) / piv;
-    if (lane == k) rdiag[k] = r;
-    if (act && lane > k) {
-      const int c0 = k / VC;                                     // first chunk that holds a column >= k
-      // all chunks are loaded unconditionally: a conditionally written register array would be
-      // demoted to local memory, and with L1 squeezed to a few KB that is an L2 round trip per access
-      V uv[NV], av[NV];
-#pragma unroll
-      for (int c = 0; c < NV; ++c) { uv[c] = *reinterpret_cast<const V*>(prow + c * VC); av[c] = *reinterpret_cast<const V*>(row + c * VC); }
-      const T l = row[k] * r;
-      // chunks right of the one holding column k: plain FMAs (independent, no selects); the
-      // boundary chunk: per-element select; chunks left of it: untouched
-#pragma unroll
-      for (int c = 0; c < NV; ++c) {
-        if (c > c0) {
-          T u[VC], a[VC];
-          vec_get<T>(uv[c], u);
-          vec_get<T>(av[c], a);
-#pragma unroll
-          for (int q = 0; q < VC; ++q) a[q] = fma(-l, u[q], a[q]);
-          *reinterpret_cast<V*>(row + c * VC) = vec_make(a);
-        } else if (c == c0) {
-          T u[VC], a[VC];
-          vec_get<T>(uv[c], u);
-          vec_get<T>(av[c], a);
-          const int kq = k - c * VC;
-#pragma unroll
-          for (int q = 0; q < VC; ++q) a[q] = (q > kq) ? fma(-l, u[q], a[q]) : ((q == kq) ? l : a[q]);
-          *reinterpret_cast<V*>(row + c * VC) = vec_make(a);
-        }
-      }
-    }
-    __syncwarp();
-  }
-  if (lane == 0) *smem_int(o_flag_i) = moved ? 1 : 0;
-}
-
-// Diagonal blocks, inverses (run after the whole factorisation, one warp per triangle, all blocks
-// in parallel): D <- [strict-lower(inv L) \ upper(inv U)] IN PLACE, by right-looking substitution.
-// The lower job only ever writes columns < lane of row `lane`, the upper job columns >= lane; the
-// 16-byte chunk that holds the diagonal is shared between them and is accessed element-wise.
-template <typename T, int MODE, int NB>
-__device__ __noinline__ void diag_inverse_lower_inplace(MPtr<T, MODE> Db, int ld) {
-  using V = typename VecOf<T>::type;
-  constexpr int VC = VecOf<T>::VC, NV = NB / VC;
-  T* const D = Db.get();
-  const int lane = threadIdx.x & 31;
-  const bool act = lane < NB;
-  T* row = D + (size_t)(act ? lane : 0) * ld;
-  const int ci = lane / VC;                      // chunk of the own diagonal
-#pragma unroll 1
-  for (int k = 0; k < NB - 1; ++k) {
-    if (act && lane > k) {                       // rows below k, columns <= k
-      const T* xk = D + (size_t)k * ld;          // row k of inv(L) (final): columns < k
-      const int cl = k / VC;
-      const T ml = row[k];
-      V xv[NV], av[NV];
-#pragma unroll
-      for (int c = 0; c < NV; ++c) { xv[c] = *reinterpret_cast<const V*>(xk + c * VC); av[c] = *reinterpret_cast<const V*>(row + c * VC); }
-#pragma unroll
-      for (int c = 0; c < NV; ++c) {
-        if (c > cl) continue;
-        T a[VC], x[VC];
-        vec_get<T>(av[c], a);
-        vec_get<T>(xv[c], x);
-        const int kq = k - c * VC;               // >= VC for chunks left of the boundary chunk
-#pragma unroll
-        for (int q = 0; q < VC; ++q) a[q] = (q < kq) ? fma(-ml, x[q], a[q]) : ((q == kq) ? -ml : a[q]);
-        if (c != ci) {
-          *reinterpret_cast<V*>(row + c * VC) = vec_make(a);
-        } else {
-#pragma unroll
-          for (int q = 0; q < VC; ++q)
-            if (q <= kq) row[c * VC + q] = a[q];
-        }
-      }
-    }
-    __syncwarp();
-  }
-}
-
-template <typename T, int MODE, int NB>
-__device__ __noinline__ void diag_inverse_upper_inplace(MPtr<T, MODE> Db, int ld, int o_rdiag) {
-  using V = typename VecOf<T>::type;
-  constexpr int VC = VecOf<T>::VC, NV = NB / VC;
-  T* const D = Db.get();
-  const T* const rdiag = smem_base<T>() + o_rdiag;
-  const int lane = threadIdx.x & 31;
-  const bool act = lane < NB;
-  T* row = D + (size_t)(act ? lane : 0) * ld;
-  const int ci = lane / VC;
-#pragma unroll 1
-  for (int kk = NB - 1; kk > 0; --kk) {
-    if (act && lane < kk) {                      // unscaled rows Z: rows above kk, columns >= kk
-      const T* zk = D + (size_t)kk * ld;         // row kk of Z (final): columns > kk
-      const int cu = kk / VC;
-      const T fu = row[kk] * rdiag[kk];
-      V zv[NV], av[NV];
-#pragma unroll
-      for (int c = 0; c < NV; ++c) { zv[c] = *reinterpret_cast<const V*>(zk + c * VC); av[c] = *reinterpret_cast<const V*>(row + c * VC); }
-#pragma unroll
-      for (int c = 0; c < NV; ++c) {
-        if (c < cu) continue;
-        T a[VC], z[VC];
-        vec_get<T>(av[c], a);
-        vec_get<T>(zv[c], z);
-        const int kq = kk - c * VC;              // < 0 for chunks right of the boundary chunk
-#pragma unroll
-        for (int q = 0; q < VC; ++q) a[q] = (q > kq) ? fma(-fu, z[q], a[q]) : ((q == kq) ? -fu : a[q]);
-        if (c != ci) {
-          *reinterpret_cast<V*>(row + c * VC) = vec_make(a);
-        } else {
-#pragma unroll
-          for (int q = 0; q < VC; ++q)
-            if (q >= kq) row[c * VC + q] = a[q];
-        }
-      }
-    }
-    __syncwarp();
-  }
-  if (act) {                                     // inv(U)[i][j] = Z[i][j] / U[i][i], inv(U)[i][i] = 1 / U[i][i]
-    const T ri = rdiag[lane];
-#pragma unroll
-    for (int c = 0; c < NV; ++c) {
-      if (c < ci) continue;
-      if (c != ci) {
-        T a[VC];
-        vec_get<T>(*reinterpret_cast<const V*>(row + c * VC), a);
-#pragma unroll
-        for (int q = 0; q < VC; ++q) a[q] *= ri;
-        *reinterpret_cast<V*>(row + c * VC) = vec_make(a);
-      } else {
-#pragma unroll
-        for (int q = 0; q < VC; ++q) {
-          const int j = c * VC + q;
-          if (j > lane) row[j] *= ri;
-          else if (j == lane) row[j] = ri;
-        }
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Panel solves of one block step by SUBSTITUTION with the L\U diagonal block (in place, one
 // register array per thread):
 //   panel_cols: U12 columns [c_lo, c_hi) of rows k0..k0+NB of `Ub`:  U12 = L11^{-1} A12  (one column
 //       per thread, left-looking: rows of L11 are read as broadcast vectors)
 //   panel_rows: L21 rows [r_lo, r_hi) of `Cb`:  L21 = A21 U11^{-1}  (one row per thread, right-looking:
 //       rows of U11 are read as broadcast vectors, rdiag = 1/diag(U11))
-// Warps 1..skip_warp do not take part (they are inverting the diagonal block).
+// tix in [0, nthr): index of this thread among the participating ones (tix < 0: not taking part).
 template <typename T, int MODE>
-__device__ __noinline__ void panel_cols(MPtr<T, MODE> Ub, int ldu, int k0, int c_lo, int c_hi, int skip_warp) {
+__device__ __noinline__ void panel_cols(MPtr<T, MODE> Ub, int ldu, int k0, int c_lo, int c_hi, int tix, int nthr) {
   using V = typename VecOf<T>::type;
   constexpr int VC = VecOf<T>::VC, NB = Blk<T>::NB;
   T* const U = Ub.get();
   const T* D = U + (size_t)k0 * ldu + k0;
-  const int warp = threadIdx.x >> 5;
-  if (warp >= 1 && warp <= skip_warp) return;                  // warps 1..skip_warp are busy elsewhere
-  const int nthr = blockDim.x - 32 * skip_warp;
-  const int tix = threadIdx.x - (warp > skip_warp ? 32 * skip_warp : 0);
+  if (tix < 0) return;
   for (int t = c_lo + tix; t < c_hi; t += nthr) {
     T a[NB];
     T* col = U + (size_t)k0 * ldu + t;
@@ -623,17 +369,15 @@ __device__ __noinline__ void panel_cols(MPtr<T, MODE> Ub, int ldu, int k0, int c
 
 template <typename T, int CMODE, int UMODE>
 __device__ __noinline__ void panel_rows(MPtr<T, CMODE> Cb, int ldc, MPtr<T, UMODE> Ub, int ldu, int k0, int r_lo,
-                                        int r_hi, int o_rdiag, int skip_warp, int tshift) {
+                                        int r_hi, int o_rdiag, int tix_, int nthr, int tshift) {
   using V = typename VecOf<T>::type;
   constexpr int VC = VecOf<T>::VC, NB = Blk<T>::NB;
   T* const C = Cb.get();
   const T* D = Ub.get() + (size_t)k0 * ldu + k0;
   const T* const rdiag = smem_base<T>() + o_rdiag;
-  const int warp = threadIdx.x >> 5;
-  if ((warp >= 1 && warp <= skip_warp) || r_hi <= r_lo) return;
-  const int nthr = blockDim.x - 32 * skip_warp;
+  if (tix_ < 0 || r_hi <= r_lo) return;
   // rotate the thread ids so that row tasks land on the threads the column tasks left idle
-  int tix = threadIdx.x - (warp > skip_warp ? 32 * skip_warp : 0) - (tshift % nthr);
+  int tix = tix_ - (tshift % nthr);
   if (tix < 0) tix += nthr;
   for (int t = r_lo + tix; t < r_hi; t += nthr) {
     T a[NB];
@@ -667,6 +411,66 @@ __device__ __noinline__ void panel_rows(MPtr<T, CMODE> Cb, int ldc, MPtr<T, UMOD
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Look-ahead pieces (ONE warp each, compact rolled loops -- see diag_lu_rot for why): the two
+// panel blocks the next diagonal block depends on. D = diagonal block k (L\U), ld its stride.
+//   lookahead_u12: block (k, k+1) = L11^{-1} A12 in place. Lane j owns COLUMN j; after each row the
+//       registers shift left by one, the finished entry goes to memory.
+//   lookahead_l21: block (k+1, k) = A21 U11^{-1} in place. Lane i owns row i; after each column the
+//       registers shift left by one (same trick as diag_lu_rot), the multiplier goes to memory.
+template <typename T, int MODE, int NB>
+__device__ __noinline__ void lookahead_u12(MPtr<T, MODE> Db, int ld) {
+  const T* const D = Db.get();
+  T* const B = Db.get() + NB;                     // block (k, k+1): same rows, next NB columns
+  const int lane = threadIdx.x & 31;
+  const int lj = lane < NB ? lane : NB - 1;
+  // lane j owns COLUMN j: the substitution needs no cross-lane traffic at all, the entries of L11
+  // are warp-uniform (broadcast) loads that do not depend on the running values
+  T a[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) a[i] = B[(size_t)i * ld + lj];
+#pragma unroll 1
+  for (int q = 0; q < NB; ++q) {
+    const T x = a[0];                              // U12[q][j] is final
+    if (lane < NB) B[(size_t)q * ld + lj] = x;
+    // L[q + i][q], i >= 1; rows past the block only reach "don't care" registers
+    const T* lc = D + (size_t)q * ld + q;
+#pragma unroll
+    for (int i = 1; i < NB; ++i) a[i - 1] = fma(-lc[(size_t)i * ld], x, a[i]);
+  }
+  __syncwarp();
+}
+
+template <typename T, int MODE, int NB>
+__device__ __noinline__ void lookahead_l21(MPtr<T, MODE> Db, int ld, int o_rdiag) {
+  using V = typename VecOf<T>::type;
+  constexpr int VC = VecOf<T>::VC, NV = NB / VC;
+  const T* const D = Db.get();
+  const T* const rdiag = smem_base<T>() + o_rdiag;
+  const int lane = threadIdx.x & 31;
+  const int li = lane < NB ? lane : NB - 1;
+  T* const row = Db.get() + (size_t)(NB + li) * ld;   // block (k+1, k): next NB rows, same columns
+  T a[NB];
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    T t[VC];
+    vec_get<T>(*reinterpret_cast<const V*>(row + c * VC), t);
+#pragma unroll
+    for (int q = 0; q < VC; ++q) a[c * VC + q] = t[q];
+  }
+  __syncwarp();                                    // all rows are in registers before any store
+#pragma unroll 1
+  for (int p = 0; p < NB; ++p) {
+    const T l = a[0] * rdiag[p];
+    if (lane < NB) row[p] = l;
+    // U[p][p + j], j >= 1; entries past the block only reach "don't care" registers
+    const T* up = D + (size_t)p * ld + p;
+#pragma unroll
+    for (int j = 1; j < NB; ++j) a[j - 1] = fma(-l, up[j], a[j]);
+  }
+  __syncwarp();
+}
+
 // Apply the block's row interchanges (rows k0..k0+NB of `Cb`) to columns [c_begin, c_end), except
 // the diagonal block's own columns when skip_diag. Each thread owns one column: no barrier between
 // its reads and writes. perm (region base, int units): perm[k0 + r] = block-local source row.
@@ -689,58 +493,105 @@ __device__ __noinline__ void apply_block_perm(MPtr<T, CMODE> Cb, int ldc, int k0
 // ---------------------------------------------------------------------------------------------
 // Factor one square region: rows/cols [0, sz) of the matrix at Ab (ld) with ncols_total columns,
 // optionally with extra "low" rows [sz, sz+nlow) held in Lb (ldl) that only carry the L panel
-// (columns [0, sz)) -- the split case's phase 1. Per block step:
-//   S1  warp 0: L\U of the diagonal block (register fast path, pivoting fallback)        | barrier
-//   S2  everyone: panel solves by substitution                                           | barrier
-//   S3  everyone: trailing update                                                        | barrier
+// (columns [0, sz)) -- the split case's phase 1.
+//
+// The diagonal block is a serial job for ONE warp (~10-16k cycles) while panels + trailing update
+// of a step keep 16 warps busy for about as long, so the two are overlapped (look-ahead): in step k
+//   warps 0,1: U12 / L21 of the NEXT block only (blocks (k,k+1), (k+1,k)), one each -> named barrier 1
+//   warp 0   : update of block (k+1,k+1) fused with its L\U factorisation (perm / flag of block k+1)
+//   warps 2+ : panels of step k for everything else -> named barrier 1
+//   warps 1+ : trailing update of everything except block (k+1,k+1)
+// and one CTA barrier closes the step. The row interchanges found in block k+1 are applied to the
+// rest of its block row (and to the shadow array Sb) at the start of step k+1.
 // The diagonal blocks are left as L\U; their inverses are formed afterwards for all blocks in
 // parallel (lu_invert_diag_blocks). rdiag is indexed by the GLOBAL row (offset o_rdiag + row0).
 // Sb (shadow_cols > 0): rows [0,sz) x [0,shadow_cols) of another shared array that must follow the
 // row interchanges (the L21 rows of the split's second half). row0: global index of this region's
 // first row (perm / rdiag position).
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 template <typename T, int MODE>
 __device__ __forceinline__ void lu_region(MPtr<T, MODE> Ab, int ld, int sz, int ncols_total, MPtr<T, 0> Lb, int ldl,
                                           int nlow, LuVec lv, int row0, long long* prof, MPtr<T, 0> Sb, int ldsh,
                                           int shadow_cols) {
   constexpr int NB = Blk<T>::NB;
+  // roles: the SMSP arbiter prefers the highest warp id, so the serial look-ahead chain runs on the
+  // LAST warp (role 0), the L21 piece on the one before (role 1, another SMSP), the bulk on the rest
+  const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int warp = nw - 1 - (threadIdx.x >> 5);                 // role index, used like a warp id below
+  const bool is_timer = warp == 2 && lane == 0;
   long long t0 = 0;
   auto lap = [&](int idx) {
-    if (prof && threadIdx.x == 0) { const long long t = clock64(); prof[idx] += t - t0; t0 = t; }
+    if (prof && is_timer) { const long long t = clock64(); prof[idx] += t - t0; t0 = t; }
   };
-  if (prof && threadIdx.x == 0) t0 = clock64();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (prof && is_timer) t0 = clock64();
   const int o_perm_i = lv.o_perm_i + row0;
   const int o_rdiag = lv.o_rdiag + row0;
-  const int* const flag = smem_int(lv.o_flag_i);
   // low rows are addressed as rows [sz, sz+nlow) of a re-based array
   const MPtr<T, 0> Lrb = Lb.plus(-(long long)sz * ldl);
-  for (int k0 = 0; k0 < sz; k0 += NB) {
-    const MPtr<T, MODE> Db = Ab.plus((long long)k0 * ld + k0);
-    if (warp == 0) {
-      diag_lu_rot<T, MODE, NB>(Db, ld, o_perm_i + k0, o_rdiag + k0, lv.o_flag_i, lv.o_stage);
-      if (prof && lane == 0) { prof[11] += 1; if (*smem_int(lv.o_flag_i)) prof[10] += 1; }
-    }
-    lap(6);
-    __syncthreads();
-    lap(9);
-    if (*flag) {
+  if (warp == 0) {
+    const long long c0 = prof ? clock64() : 0;
+    diag_lu_rot<T, MODE, NB>(Ab, ld, o_perm_i, o_rdiag, lv.o_flag_i, lv.o_stage, 0);
+    if (prof && lane == 0) { prof[11] += 1; if (*smem_int(lv.o_flag_i)) prof[10] += 1; prof[6] += clock64() - c0; }
+  }
+  __syncthreads();
+  lap(13);
+  for (int k0 = 0, kb = 0; k0 < sz; k0 += NB, ++kb) {
+    const int r0 = k0 + NB;
+    const bool has_next = r0 < sz;
+    if (*smem_int(lv.o_flag_i + (kb & 1))) {
       apply_block_perm<T, MODE>(Ab, ld, k0, o_perm_i, 0, ncols_total, 1);
       if (shadow_cols > 0) apply_block_perm<T, 0>(Sb, ldsh, k0, o_perm_i, 0, shadow_cols, 0);
       __syncthreads();
     }
-    const int r0 = k0 + NB;
-    panel_cols<T, MODE>(Ab, ld, k0, r0, ncols_total, 0);
-    panel_rows<T, MODE, MODE>(Ab, ld, Ab, ld, k0, r0, sz, o_rdiag + k0, 0, max(ncols_total - r0, 0));
-    if (nlow > 0)
-      panel_rows<T, 0, MODE>(Lrb, ldl, Ab, ld, k0, sz, sz + nlow, o_rdiag + k0, 0,
-                             max(ncols_total - r0, 0) + max(sz - r0, 0));
+    lap(13);                                                     // (a barrier blocks at its first consumer)
+    if (has_next && warp < 2) {
+      // ---- look-ahead group: warp 0 -> U12 block, warp 1 -> L21 block (in parallel)
+      const long long c0 = prof ? clock64() : 0;
+      const MPtr<T, MODE> Db = Ab.plus((long long)k0 * ld + k0);
+      if (warp == 0) lookahead_u12<T, MODE, NB>(Db, ld);
+      else lookahead_l21<T, MODE, NB>(Db, ld, o_rdiag + k0);
+      named_bar_sync(2, 64);                                     // the two pieces see each other
+      if (warp == 0) {
+        named_bar_arrive(1, blockDim.x);                         // release them to everyone (warp 1 syncs below)
+        const long long c1 = prof ? clock64() : 0;
+        diag_lu_rot<T, MODE, NB>(Ab.plus((long long)r0 * ld + r0), ld, o_perm_i + r0, o_rdiag + r0,
+                                 lv.o_flag_i + ((kb + 1) & 1), lv.o_stage, 1);
+        if (prof && lane == 0) {
+          prof[11] += 1; if (*smem_int(lv.o_flag_i + ((kb + 1) & 1))) prof[10] += 1;
+          const long long c2 = clock64(); prof[12] += c1 - c0; prof[6] += c2 - c1;
+        }
+      }
+    }
+    if (!(has_next && warp == 0)) {
+      // ---- panels: warps 2+ (all warps in the last step); update: warps 1+ (all in the last step)
+      const int pw = has_next ? warp - 2 : warp, npw = has_next ? nw - 2 : nw;
+      const int tix = pw < 0 ? -1 : pw * 32 + lane, nthr = npw * 32;
+      const int wid = has_next ? warp - 1 : warp, nwk = has_next ? nw - 1 : nw;
+      const int skip = has_next ? NB : 0;                       // block column / row k+1: look-ahead group
+      const int ncol_tasks = max(ncols_total - r0 - skip, 0), nrow_tasks = max(sz - r0 - skip, 0);
+      panel_cols<T, MODE>(Ab, ld, k0, r0 + skip, ncols_total, tix, nthr);
+      panel_rows<T, MODE, MODE>(Ab, ld, Ab, ld, k0, r0 + skip, sz, o_rdiag + k0, tix, nthr, ncol_tasks);
+      if (nlow > 0)
+        panel_rows<T, 0, MODE>(Lrb, ldl, Ab, ld, k0, sz, sz + nlow, o_rdiag + k0, tix, nthr, ncol_tasks + nrow_tasks);
+      if (has_next) named_bar_sync(1, blockDim.x); else __syncthreads();
+      lap(7);
+      // trailing update minus block (k+1,k+1): block row k+1 right of it, the rows below, the low rows
+      int dealt = 0;
+      if (has_next) {
+        dealt += rank_nb_update_auto<T, MODE, MODE>(Ab, ld, Ab, ld, k0, r0, r0 + NB, r0 + NB, ncols_total, wid, nwk, dealt);
+        dealt += rank_nb_update_auto<T, MODE, MODE>(Ab, ld, Ab, ld, k0, r0 + NB, sz, r0, ncols_total, wid, nwk, dealt);
+      }
+      if (nlow > 0) dealt += rank_nb_update_auto<T, 0, MODE>(Lrb, ldl, Ab, ld, k0, sz, sz + nlow, r0, sz, wid, nwk, dealt);
+      lap(8);
+    }
     __syncthreads();
-    lap(7);
-    // trailing update: rows [r0, sz) x cols [r0, ncols_total)  and  low rows [sz, sz+nlow) x cols [r0, sz)
-    rank_nb_update_auto<T, MODE, MODE>(Ab, ld, Ab, ld, k0, r0, sz, r0, ncols_total);
-    if (nlow > 0) rank_nb_update_auto<T, 0, MODE>(Lrb, ldl, Ab, ld, k0, sz, sz + nlow, r0, sz);
-    __syncthreads();
-    lap(8);
+    lap(13);                                                     // warps 1+ waiting for the look-ahead warp
   }
 }
 

@@ -31,7 +31,7 @@ struct Plan {
 
 // phases for the optional cycle counters
 enum { PH_PREFACTOR = 0, PH_LOADT, PH_LU, PH_SOLVE, PH_RESID, PH_STEP, PH_LU_DIAG, PH_LU_PANEL, PH_LU_UPDATE,
-       PH_LU_DIAGWAIT, PH_LU_SLOWDIAG, PH_LU_BLOCKS, PH_COUNT };
+       PH_LU_DIAGWAIT, PH_LU_SLOWDIAG, PH_LU_BLOCKS, PH_LU_AHEAD, PH_LU_WAIT, PH_COUNT };
 
 template <typename T>
 struct Vecs {

@@ -298,7 +298,7 @@ extern "C" int lcpb200_backward(lcpb200_handle_t h, int B, const void* Q, const 
 
 extern "C" int lcpb200_profile(lcpb200_handle_t h, int enable, long long* out) {
   // Development aid: per-phase SM cycle counters (thread 0 of every CTA), summed over CTAs.
-  // enable = 1 allocates + zeroes the counters, 0 frees them; `out` (PH_COUNT = 12 values:
+  // enable = 1 allocates + zeroes the counters, 0 frees them; `out` (PH_COUNT = 14 values:
   // prefactor, load T, LU, KKT solves, residuals, step rules) receives the current sums.
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->device));

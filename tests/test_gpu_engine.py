@@ -24,7 +24,9 @@ def test_engine_replays_reference_world(name):
         else:
             out = eng.post_stabilization(world)
         ref = torch.from_numpy(rec["result"]).reshape(out.shape)
-        err = (out.cpu() - ref).norm() / ref.norm().clamp_min(1e-12)
+        # the chain scene rests on the ground: its new velocities are round-off (1e-16) around zero,
+        # so the error is taken relative to max(|ref|, 1) (velocities here are O(1..100))
+        err = (out.cpu() - ref).norm() / ref.norm().clamp_min(1.0)
         worst = max(worst, float(err))
     assert worst < 1e-6, worst
 
