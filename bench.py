@@ -274,7 +274,9 @@ def run_b200(args, rank, world, local_rank):
         "kernels": {"lcp_forward_kernel<float>_ms": fwd_ms, "lcp_backward_kernel<float>_ms": bwd_ms},
         "roofline": {"bound": "hbm", "kernel": "lcp_forward_kernel<float>",
                      "achieved": stream_gbs, "peak": peak, "unit": "GB/s", "frac": stream_gbs / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": measured_traffic(B), "peak_source": peak_src,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one forward launch, ncu --set full "
+                                       "(profiles/*_fwd_traffic.json), scaled by batch",
                      "definition": "north_star per-iteration HBM roofline: (K+1) x (m^2+mn+n^2) x 4 B per solve "
                                    "(the KKT block streamed once per factorisation) / forward-kernel time",
                      "resident_bytes_gbs": alg["b_fwd_resident"] * B / (fwd_ms * 1e-3) / 1e9,
@@ -289,6 +291,17 @@ def run_b200(args, rank, world, local_rank):
                                 "sample": "%d of the 4096 scenes, fwd+bwd, %.1f s, as-is reference semantics "
                                           "(incl. util.py:86-90 pivot loop)" % (args.cpu_sample, dt)}
     print(json.dumps(line), flush=True)
+
+
+def measured_traffic(batch):
+    """DRAM bytes per forward launch from the newest committed ncu capture (profiles/rNN_fwd_traffic.json)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r*_fwd_traffic.json")))
+    if not files:
+        return None
+    with open(files[-1]) as f:
+        d = json.load(f)
+    return d["dram_bytes_per_launch"] * batch / d["batch"]
 
 
 def main():
