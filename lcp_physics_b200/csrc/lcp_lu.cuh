@@ -238,15 +238,16 @@ __device__ __noinline__ void diag_lu_rot(MPtr<T, MODE> Db, int ld, int o_perm_i,
       }
     }
   }
+  if (lane < NB) perm[lane] = lane;
+  const float tau = (sizeof(T) == 4) ? 1e-4f : 1e-8f;
+  bool moved = false;
+  T myr = 0;
+  // rinv: every lane keeps the reciprocal of its leading entry ready (computed right after a row
+  // update, off the step-to-step dependence chain); the pivot lane publishes it with its row and
+  // its row scale rm = max |row| of the block row before elimination.
   T rm = 0;
 #pragma unroll
   for (int j = 0; j < NB; ++j) rm = fmax(rm, fabs(a[j]));
-  if (lane < NB) perm[lane] = lane;
-  const T tau = (sizeof(T) == 4) ? T(1e-4) : T(1e-8);
-  bool moved = false;
-  T myr = 0;
-  // every lane keeps the reciprocal of its leading entry ready: the pivot lane publishes it with
-  // its row, which takes the reciprocal's latency off the step-to-step dependence chain
   T rinv = fast_rcp(a[0]);
 #pragma unroll 1
   for (int k = 0; k < NB; ++k) {
@@ -262,8 +263,8 @@ __device__ __noinline__ void diag_lu_rot(MPtr<T, MODE> Db, int ld, int o_perm_i,
         for (int q = 0; q < VC; ++q) t[q] = a[c * VC + q];
         *reinterpret_cast<V*>(st + c * VC) = vec_make(t);
       }
-      st[NB] = rm;
-      st[NB + 1] = rinv;
+      st[NB] = rinv;
+      st[NB + 1] = rm;
     }
     __syncwarp();
 #pragma unroll
@@ -274,9 +275,20 @@ __device__ __noinline__ void diag_lu_rot(MPtr<T, MODE> Db, int ld, int o_perm_i,
       for (int q = 0; q < VC; ++q) u[c * VC + q] = t[q];
     }
     T piv = u[0];
-    const T rs = st[NB];
-    T r = st[NB + 1];
-    if (!(fabs(piv) >= tau * rs && fabs(piv) > T(0))) {          // rare, warp-uniform
+    T r = st[NB];
+    const T rs = st[NB + 1];
+    // Threshold partial pivoting, three tiers: (1) pivot >= tau * row scale: accept (the common
+    // case, nothing extra on the chain); (2) else compare with the pivot column's largest candidate,
+    // one REDUX on the float bit patterns (non-negative floats order like unsigned integers);
+    // (3) only if that fails too search the arg-max row and interchange.
+    bool suspect = !(fabs(piv) >= T(tau) * rs && fabs(piv) > T(0));
+    if (suspect) {
+      float f = fabsf((float)a[0]);
+      if (f != f) f = INFINITY;
+      const unsigned cb = __reduce_max_sync(FULL, (lane >= k && lane < NB) ? __float_as_uint(f) : 0u);
+      suspect = !(fabsf((float)piv) >= 2.f * tau * __uint_as_float(cb) && fabs(piv) > T(0));
+    }
+    if (suspect) {                                               // rare, warp-uniform
       T best = (lane >= k && lane < NB) ? fabs(a[0]) : T(-1);
       if (best != best) best = INFINITY;
       int bi = lane;
@@ -286,8 +298,8 @@ __device__ __noinline__ void diag_lu_rot(MPtr<T, MODE> Db, int ld, int o_perm_i,
         const int oi = __shfl_xor_sync(FULL, bi, o);
         if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
       }
-      if (bi != k && !(fabs(piv) >= tau * best && fabs(piv) > T(0))) {
-        // interchange rows k and bi: live registers (same shift on both), scale, L part, perm
+      if (bi != k && !(fabs(piv) >= T(tau) * best && fabs(piv) > T(0))) {
+        // interchange rows k and bi: live registers (same shift on both), L part, perm
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
           const T fk = __shfl_sync(FULL, a[j], k), fb = __shfl_sync(FULL, a[j], bi);
@@ -520,14 +532,12 @@ __device__ __forceinline__ void lu_region(MPtr<T, MODE> Ab, int ld, int sz, int 
                                           int nlow, LuVec lv, int row0, long long* prof, MPtr<T, 0> Sb, int ldsh,
                                           int shadow_cols) {
   constexpr int NB = Blk<T>::NB;
-  // Roles. The serial look-ahead chain (role 0) is latency-bound on shared-memory round trips, so it
-  // gets the LAST warp (the SMSP arbiter prefers the highest warp id) and, when there are enough
-  // warps, its SMSP to itself and the L21-piece warp (role 1): the other warps of that SMSP sit the
-  // overlapped steps out ("quiet") -- the bulk loses 2 of 14 warps, the chain no longer queues its
-  // loads behind theirs.
+  // Roles. The serial look-ahead chain (role 0) runs on the LAST warp (the SMSP arbiter prefers the
+  // highest warp id), the L21-piece warp (role 1) on another SMSP, the bulk on the rest. (Keeping
+  // the chain's SMSP free of bulk warps was measured: chain -5%, bulk -12%, net loss.)
   const int lane = threadIdx.x & 31, nw = blockDim.x >> 5, pw = threadIdx.x >> 5;
-  const int chain_w = nw - 1, piece_w = nw >= 8 ? nw - 5 : nw - 2;
-  auto is_quiet = [&](int w) { return nw >= 12 && (w & 3) == (chain_w & 3) && w != chain_w && w != piece_w; };
+  const int chain_w = nw - 1, piece_w = nw - 2;
+  auto is_quiet = [&](int) { return false; };
   int bidx = 0, nbulk = 0;
   for (int w = 0; w < nw; ++w) {
     const bool bulk = w != chain_w && w != piece_w && !is_quiet(w);

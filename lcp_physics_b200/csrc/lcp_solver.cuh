@@ -42,6 +42,7 @@ struct Vecs {
   T *dxa, *dsa, *dza, *dya;
   T *dxc, *dsc, *dzc, *dyc;
   T *rs2;
+  T *qinv;                    // n: 1/diag(Q) when Q is diagonal (SceneCtx::qdiag)
   T *scratch;                 // max(4 nt, mp) elements
   T *red;                     // 128 elements
   int *perm;                  // mp ints
@@ -57,7 +58,7 @@ struct Vecs {
     LCPB200_TAKE(tn, n); LCPB200_TAKE(tn2, n);
     LCPB200_TAKE(dxa, n); LCPB200_TAKE(dsa, mp); LCPB200_TAKE(dza, mp); LCPB200_TAKE(dya, e);
     LCPB200_TAKE(dxc, n); LCPB200_TAKE(dsc, mp); LCPB200_TAKE(dzc, mp); LCPB200_TAKE(dyc, e);
-    LCPB200_TAKE(rs2, mp);
+    LCPB200_TAKE(rs2, mp); LCPB200_TAKE(qinv, n);
     LCPB200_TAKE(scratch, 4 * nt > mp ? 4 * nt : mp); LCPB200_TAKE(red, 128);
     { T* pp; LCPB200_TAKE(pp, mp); perm = reinterpret_cast<int*>(pp); }
     LCPB200_TAKE(stage, 4); LCPB200_TAKE(rdiag, mp);
@@ -77,6 +78,7 @@ struct SceneCtx {
   TView<T, MODE> tv;
   T *R, *X, *XA, *S11, *Vm, *W;
   bool Rsaved;                // R points at a matrix saved by the forward pass (read-only)
+  bool qdiag;                 // Q is diagonal: Q^{-1} v is an element-wise product with Vecs::qinv
   int stage_ld;               // > 0: G may be staged in T's shared region with this leading dimension
   const T* Gsrc;              // this scene's G in global memory
   int* lu_flag;
@@ -251,12 +253,14 @@ __device__ __noinline__ bool prefactor(SceneCtx<T, MODE>& c, int* flag) {
   int offdiag = 0;
   for (int t = tid; t < n * n; t += NT) { const int i = t / n, j = t - i * n; if (i != j && c.Q[t] != T(0)) offdiag = 1; }
   offdiag = __syncthreads_or(offdiag);
+  c.qdiag = !offdiag;
   if (!offdiag) {
     for (int t = tid; t < n * n; t += NT) {
       const int i = t / n, j = t - i * n;
       T val = 0;
       if (i == j) { const T q = c.Q[t]; if (!(q != T(0) && isfinite((double)q))) *flag = 1; val = T(1) / q; }
       c.Qi[(size_t)i * c.ldQi + j] = val;
+      if (i == j) v.qinv[i] = val;
     }
     __syncthreads();
   } else {
@@ -330,27 +334,54 @@ __device__ __noinline__ void factor_kkt(SceneCtx<T, MODE>& c) {
   const bool vec_ok = (m % VC == 0) && ((reinterpret_cast<uintptr_t>(c.R) & 15) == 0);
   if (vec_ok) {
     const int mv = mp / VC;
+    constexpr int UB = 8;                          // independent L2 loads in flight per thread
     // main rows [0,m1) x all columns
-#pragma unroll 4
-    for (int t = tid; t < m1 * mv; t += NT) {
-      const int i = t / mv, j = (t - i * mv) * VC;
-      T val[VC];
-      if (i < m && j < m) vec_get<T>(*reinterpret_cast<const V*>(c.R + (size_t)i * m + j), val);
-      else { for (int q = 0; q < VC; ++q) val[q] = 0; }
+    const int tot1 = m1 * mv;
+    for (int t0 = tid; t0 < tot1; t0 += NT * UB) {
+      V val[UB];
 #pragma unroll
-      for (int q = 0; q < VC; ++q)
-        if (j + q == i) val[q] += dinv[i];
-      *reinterpret_cast<V*>(tmain + (size_t)i * c.tv.ld + j) = vec_make(val);
+      for (int u = 0; u < UB; ++u) {
+        const int t = t0 + u * NT;
+        const int i = t / mv, j = (t - i * mv) * VC;
+        T z[VC];
+#pragma unroll
+        for (int q = 0; q < VC; ++q) z[q] = 0;
+        val[u] = (t < tot1 && i < m && j < m) ? *reinterpret_cast<const V*>(c.R + (size_t)i * m + j) : vec_make(z);
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int t = t0 + u * NT;
+        if (t >= tot1) continue;
+        const int i = t / mv, j = (t - i * mv) * VC;
+        T w[VC];
+        vec_get<T>(val[u], w);
+#pragma unroll
+        for (int q = 0; q < VC; ++q)
+          if (j + q == i) w[q] += dinv[i];
+        *reinterpret_cast<V*>(tmain + (size_t)i * c.tv.ld + j) = vec_make(w);
+      }
     }
     // low rows [m1,mp) x columns [0,m1)
     const int m1v = m1 / VC;
-#pragma unroll 4
-    for (int t = tid; t < (mp - m1) * m1v; t += NT) {
-      const int i = m1 + t / m1v, j = (t % m1v) * VC;
-      T val[VC];
-      if (i < m && j < m) vec_get<T>(*reinterpret_cast<const V*>(c.R + (size_t)i * m + j), val);
-      else { for (int q = 0; q < VC; ++q) val[q] = 0; }
-      *reinterpret_cast<V*>(tlow + (size_t)(i - m1) * c.tv.ldl + j) = vec_make(val);
+    const int tot2 = (mp - m1) * m1v;
+    for (int t0 = tid; t0 < tot2; t0 += NT * UB) {
+      V val[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int t = t0 + u * NT;
+        const int i = m1 + t / m1v, j = (t % m1v) * VC;
+        T z[VC];
+#pragma unroll
+        for (int q = 0; q < VC; ++q) z[q] = 0;
+        val[u] = (t < tot2 && i < m && j < m) ? *reinterpret_cast<const V*>(c.R + (size_t)i * m + j) : vec_make(z);
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int t = t0 + u * NT;
+        if (t >= tot2) continue;
+        const int i = m1 + t / m1v, j = (t % m1v) * VC;
+        *reinterpret_cast<V*>(tlow + (size_t)(i - m1) * c.tv.ldl + j) = val[u];
+      }
     }
   } else {
     for (int t = tid; t < m1 * mp; t += NT) {
@@ -394,7 +425,12 @@ __device__ __noinline__ void solve_kkt(SceneCtx<T, MODE>& c, int o_rx, int o_rs,
   T* dx = sb + o_dx; T* ds = sb + o_ds; T* dz = sb + o_dz; T* dy = sb + o_dy;
   T* t = v.tn;                                                   // Q^{-1} rx      :333
   if (rx) {
-    gemv_rows_v(c.Qi, c.ldQi, n, n, rx, [&](int i, T a) { t[i] = a; });
+    if (c.qdiag) {
+      for (int i = tid; i < n; i += NT) t[i] = v.qinv[i] * rx[i];
+      __syncthreads();
+    } else {
+      gemv_rows_v(c.Qi, c.ldQi, n, n, rx, [&](int i, T a) { t[i] = a; });
+    }
     gemv_rows_v(c.G, c.ldG, m, n, t, [&](int i, T a) { v.hz[i] = a + rs[i] / d[i] - (rz ? rz[i] : T(0)); });   // :337-340
     if (e > 0) gemv_rows_v(c.A, n, e, n, t, [&](int i, T a) { v.hy[i] = a - (ry ? ry[i] : T(0)); });
   } else {
@@ -417,7 +453,12 @@ __device__ __noinline__ void solve_kkt(SceneCtx<T, MODE>& c, int o_rx, int o_rs,
   T* g1 = v.tn2;                                                 // :344-349
   gemv_cols_v(c.G, c.ldG, m, n, dz, v.scratch, [&](int j, T a) { g1[j] = -(rx ? rx[j] : T(0)) - a; });
   if (e > 0) gemv_cols_v(c.A, n, e, n, dy, v.scratch, [&](int j, T a) { g1[j] -= a; });
-  gemv_rows_v(c.Qi, c.ldQi, n, n, g1, [&](int i, T a) { dx[i] = a; });
+  if (c.qdiag) {
+    for (int i = tid; i < n; i += NT) dx[i] = v.qinv[i] * g1[i];
+    __syncthreads();
+  } else {
+    gemv_rows_v(c.Qi, c.ldQi, n, n, g1, [&](int i, T a) { dx[i] = a; });
+  }
 }
 
 // ------------------------------------------------------------------ get_step (pdipm.py:182-186), per scene
@@ -468,7 +509,7 @@ __device__ void setup_ctx(SceneCtx<T, MODE>& c, const Plan& P, T* sm, T* ws, int
   c.tv.u12 = ws + P.w_U12;
   c.R = ws + P.w_R; c.X = ws + P.w_X; c.XA = ws + P.w_XA; c.S11 = ws + P.w_S11;
   c.Vm = ws + P.w_V; c.W = ws + P.w_W;
-  c.Rsaved = false; c.stage_ld = P.stage_ld; c.Gsrc = nullptr;
+  c.Rsaved = false; c.qdiag = false; c.stage_ld = P.stage_ld; c.Gsrc = nullptr;
   c.lu_flag = lu_flag;
   c.prof = prof ? prof + (size_t)blockIdx.x * PH_COUNT : nullptr;
   Vecs<T> v = c.vecs();
