@@ -60,7 +60,7 @@ struct TView {
 // Shared vectors used by the factorisation. *_i offsets are in 4-byte ints from the start of the
 // shared array, the others in elements of T.
 struct LuVec {
-  int o_perm_i, o_flag_i, o_rmaxs, o_rdiag, o_stage, lds;
+  int o_perm_i, o_flag_i, o_rmaxs, o_rdiag, o_stage, o_lt, ldlt, lds;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -201,13 +201,115 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // Measured (DESIGN.md "Pivoting"): eager swaps HURT fp32 trajectory parity, never swapping leaves
 // exact-zero pivots on converged scenes.
 // Outputs: D = L\U in place, rdiag[j] = 1/U[j][j], perm[i] = source row of row i, *flag = moved.
+// Steps [k_begin, k_end) of the rolled factorisation with W live columns: at step k only NB - k <= W
+// leading registers of a row are live, so the row broadcast and the row update touch W entries only
+// (the caller runs four phases W = NB, 3NB/4, NB/2, NB/4: a single warp issues ~1 instruction per
+// 3 cycles, instruction count is what the chain costs).
+template <typename T, int NB, int W>
+__device__ __forceinline__ void diag_rot_steps(int k_begin, int k_end, T (&a)[NB], T (&u)[NB], T& rinv, T& rm, T& myr,
+                                               bool& moved, T* D, int ld, T* stage, int* perm, T* Lt, int ldlt) {
+  using V = typename VecOf<T>::type;
+  constexpr int VC = VecOf<T>::VC, WV = W / VC, SL = NB + VC;
+  const int lane = threadIdx.x & 31;
+  const float tau = (sizeof(T) == 4) ? 1e-4f : 1e-8f;
+#pragma unroll 1
+  for (int k = k_begin; k < k_end; ++k) {
+    T* const st = stage + (k & 1) * SL;
+    {
+      // the pivot row is broadcast through shared memory: one predicated vector store per chunk by
+      // the pivot lane (a branch around the group costs a divergence round trip), broadcast loads by all
+      const bool mine = lane == k;
+#pragma unroll
+      for (int c = 0; c < WV; ++c) {
+        T t[VC];
+#pragma unroll
+        for (int q = 0; q < VC; ++q) t[q] = a[c * VC + q];
+        if (mine) *reinterpret_cast<V*>(st + c * VC) = vec_make(t);
+      }
+      if (mine) st[NB] = rinv;
+      if (mine) st[NB + 1] = rm;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < WV; ++c) {
+      T t[VC];
+      vec_get<T>(*reinterpret_cast<const V*>(st + c * VC), t);
+#pragma unroll
+      for (int q = 0; q < VC; ++q) u[c * VC + q] = t[q];
+    }
+    T piv = u[0];
+    T r = st[NB];
+    const T rs = st[NB + 1];
+    // Threshold partial pivoting, three tiers: (1) pivot >= tau * row scale: accept (the common
+    // case, nothing extra on the chain); (2) else compare with the pivot column's largest candidate,
+    // one REDUX on the float bit patterns (non-negative floats order like unsigned integers);
+    // (3) only if that fails too search the arg-max row and interchange.
+    bool suspect = !(fabs(piv) >= T(tau) * rs && fabs(piv) > T(0));
+    if (suspect) {
+      float f = fabsf((float)a[0]);
+      if (f != f) f = INFINITY;
+      const unsigned cb = __reduce_max_sync(FULL, (lane >= k && lane < NB) ? __float_as_uint(f) : 0u);
+      suspect = !(fabsf((float)piv) >= 2.f * tau * __uint_as_float(cb) && fabs(piv) > T(0));
+    }
+    if (suspect) {                                               // rare, warp-uniform
+      T best = (lane >= k && lane < NB) ? fabs(a[0]) : T(-1);
+      if (best != best) best = INFINITY;
+      int bi = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const T ov = __shfl_xor_sync(FULL, best, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (bi != k && !(fabs(piv) >= T(tau) * best && fabs(piv) > T(0))) {
+        // interchange rows k and bi: live registers (same shift on both), scale, L part (both
+        // copies), perm
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+          const T fk = __shfl_sync(FULL, a[j], k), fb = __shfl_sync(FULL, a[j], bi);
+          if (lane == k) a[j] = fb; else if (lane == bi) a[j] = fk;
+          u[j] = fb;                                               // the new pivot row
+        }
+        {
+          const T fk = __shfl_sync(FULL, rm, k), fb = __shfl_sync(FULL, rm, bi);
+          if (lane == k) rm = fb; else if (lane == bi) rm = fk;
+        }
+        if (lane < k) {
+          const T t0 = D[(size_t)k * ld + lane], t1 = D[(size_t)bi * ld + lane];
+          D[(size_t)k * ld + lane] = t1;
+          D[(size_t)bi * ld + lane] = t0;
+          Lt[(size_t)lane * ldlt + k] = t1;
+          Lt[(size_t)lane * ldlt + bi] = t0;
+        }
+        if (lane == 0) { const int p0 = perm[k]; perm[k] = perm[bi]; perm[bi] = p0; }
+        moved = true;
+        __syncwarp();
+        piv = u[0];
+        r = fast_rcp(piv);
+      }
+    }
+    if (lane == k) myr = r;
+    const bool alive = lane > k && lane < NB;
+    const T l = a[0] * r;
+    if (alive) D[(size_t)lane * ld + k] = l;                     // multiplier: final entry of L
+    if (alive) Lt[(size_t)k * ldlt + lane] = l;                  // ... and of the transposed copy
+#pragma unroll
+    for (int j = 1; j < W; ++j)
+      if (alive) a[j - 1] = fma(-l, u[j], a[j]);
+    rinv = fast_rcp(a[0]);
+  }
+}
+
+// Lt: transposed copy of the strictly-lower part (Lt[k][i] = L[i][k], leading dimension ldlt), so
+// that the look-ahead U12 piece reads columns of L as contiguous vectors.
 template <typename T, int MODE, int NB>
 __device__ __noinline__ void diag_lu_rot(MPtr<T, MODE> Db, int ld, int o_perm_i, int o_rdiag, int o_flag_i,
-                                         int o_stage, int fuse_update) {
+                                         int o_stage, int o_lt, int ldlt, int fuse_update) {
   using V = typename VecOf<T>::type;
-  constexpr int VC = VecOf<T>::VC, NV = NB / VC, SL = NB + VC;
+  constexpr int VC = VecOf<T>::VC, NV = NB / VC;
   T* const D = Db.get();
-  T* const stage = smem_base<T>() + o_stage;     // 2 x (NB + VC): the pivot row + its scale, double-buffered
+  T* const stage = smem_base<T>() + o_stage;     // 2 x (NB + VC): pivot row + reciprocal + row scale
+  T* const Lt = smem_base<T>() + o_lt;
   int* const perm = smem_int(o_perm_i);
   const int lane = threadIdx.x & 31;
   const int li = lane < NB ? lane : NB - 1;      // lanes >= NB mirror the last row and never store
@@ -239,7 +341,6 @@ __device__ __noinline__ void diag_lu_rot(MPtr<T, MODE> Db, int ld, int o_perm_i,
     }
   }
   if (lane < NB) perm[lane] = lane;
-  const float tau = (sizeof(T) == 4) ? 1e-4f : 1e-8f;
   bool moved = false;
   T myr = 0;
   // rinv: every lane keeps the reciprocal of its leading entry ready (computed right after a row
@@ -249,88 +350,11 @@ __device__ __noinline__ void diag_lu_rot(MPtr<T, MODE> Db, int ld, int o_perm_i,
 #pragma unroll
   for (int j = 0; j < NB; ++j) rm = fmax(rm, fabs(a[j]));
   T rinv = fast_rcp(a[0]);
-#pragma unroll 1
-  for (int k = 0; k < NB; ++k) {
-    T* const st = stage + (k & 1) * SL;
-    // the pivot row is broadcast through shared memory (8 vector stores by one lane, 8 broadcast
-    // vector loads by all): a warp-wide SHFL issues once per 4 cycles, 31 of them per step were
-    // the bottleneck of the shuffle variant.
-    if (lane == k) {
-#pragma unroll
-      for (int c = 0; c < NV; ++c) {
-        T t[VC];
-#pragma unroll
-        for (int q = 0; q < VC; ++q) t[q] = a[c * VC + q];
-        *reinterpret_cast<V*>(st + c * VC) = vec_make(t);
-      }
-      st[NB] = rinv;
-      st[NB + 1] = rm;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int c = 0; c < NV; ++c) {
-      T t[VC];
-      vec_get<T>(*reinterpret_cast<const V*>(st + c * VC), t);
-#pragma unroll
-      for (int q = 0; q < VC; ++q) u[c * VC + q] = t[q];
-    }
-    T piv = u[0];
-    T r = st[NB];
-    const T rs = st[NB + 1];
-    // Threshold partial pivoting, three tiers: (1) pivot >= tau * row scale: accept (the common
-    // case, nothing extra on the chain); (2) else compare with the pivot column's largest candidate,
-    // one REDUX on the float bit patterns (non-negative floats order like unsigned integers);
-    // (3) only if that fails too search the arg-max row and interchange.
-    bool suspect = !(fabs(piv) >= T(tau) * rs && fabs(piv) > T(0));
-    if (suspect) {
-      float f = fabsf((float)a[0]);
-      if (f != f) f = INFINITY;
-      const unsigned cb = __reduce_max_sync(FULL, (lane >= k && lane < NB) ? __float_as_uint(f) : 0u);
-      suspect = !(fabsf((float)piv) >= 2.f * tau * __uint_as_float(cb) && fabs(piv) > T(0));
-    }
-    if (suspect) {                                               // rare, warp-uniform
-      T best = (lane >= k && lane < NB) ? fabs(a[0]) : T(-1);
-      if (best != best) best = INFINITY;
-      int bi = lane;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const T ov = __shfl_xor_sync(FULL, best, o);
-        const int oi = __shfl_xor_sync(FULL, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-      }
-      if (bi != k && !(fabs(piv) >= T(tau) * best && fabs(piv) > T(0))) {
-        // interchange rows k and bi: live registers (same shift on both), L part, perm
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-          const T fk = __shfl_sync(FULL, a[j], k), fb = __shfl_sync(FULL, a[j], bi);
-          if (lane == k) a[j] = fb; else if (lane == bi) a[j] = fk;
-          u[j] = fb;                                               // the new pivot row
-        }
-        {
-          const T fk = __shfl_sync(FULL, rm, k), fb = __shfl_sync(FULL, rm, bi);
-          if (lane == k) rm = fb; else if (lane == bi) rm = fk;
-        }
-        if (lane < k) {
-          const T t0 = D[(size_t)k * ld + lane], t1 = D[(size_t)bi * ld + lane];
-          D[(size_t)k * ld + lane] = t1;
-          D[(size_t)bi * ld + lane] = t0;
-        }
-        if (lane == 0) { const int p0 = perm[k]; perm[k] = perm[bi]; perm[bi] = p0; }
-        moved = true;
-        __syncwarp();
-        piv = u[0];
-        r = fast_rcp(piv);
-      }
-    }
-    if (lane == k) myr = r;
-    const bool alive = lane > k && lane < NB;
-    const T l = a[0] * r;
-    if (alive) D[(size_t)lane * ld + k] = l;                     // multiplier: final entry of L
-#pragma unroll
-    for (int j = 1; j < NB; ++j)
-      if (alive) a[j - 1] = fma(-l, u[j], a[j]);
-    rinv = fast_rcp(a[0]);
-  }
+  constexpr int Q4 = NB / 4;
+  diag_rot_steps<T, NB, NB>(0, Q4, a, u, rinv, rm, myr, moved, D, ld, stage, perm, Lt, ldlt);
+  diag_rot_steps<T, NB, 3 * Q4>(Q4, 2 * Q4, a, u, rinv, rm, myr, moved, D, ld, stage, perm, Lt, ldlt);
+  diag_rot_steps<T, NB, 2 * Q4>(2 * Q4, 3 * Q4, a, u, rinv, rm, myr, moved, D, ld, stage, perm, Lt, ldlt);
+  diag_rot_steps<T, NB, Q4>(3 * Q4, NB, a, u, rinv, rm, myr, moved, D, ld, stage, perm, Lt, ldlt);
   // row i stopped shifting after step i: a[j] = U[i][i + j]
   if (lane < NB) {
 #pragma unroll
@@ -425,31 +449,54 @@ __device__ __noinline__ void panel_rows(MPtr<T, CMODE> Cb, int ldc, MPtr<T, UMOD
 
 // ---------------------------------------------------------------------------------------------
 // Look-ahead pieces (ONE warp each, compact rolled loops -- see diag_lu_rot for why): the two
-// panel blocks the next diagonal block depends on. D = diagonal block k (L\U), ld its stride.
-//   lookahead_u12: block (k, k+1) = L11^{-1} A12 in place. Lane j owns COLUMN j; after each row the
-//       registers shift left by one, the finished entry goes to memory.
-//   lookahead_l21: block (k+1, k) = A21 U11^{-1} in place. Lane i owns row i; after each column the
-//       registers shift left by one (same trick as diag_lu_rot), the multiplier goes to memory.
+// panel blocks the next diagonal block depends on. Both are private triangular solves per lane
+// (no cross-lane traffic): lane t holds NB running values a[j] in registers, pivot p finalises
+// x = a[p] (* scale[p]), and a[j] -= x * coef[p][j] for j > p, with the coefficient rows read as
+// broadcast vector loads. Pivots go in groups of VC so that the loads stay vector-aligned; after a
+// group the registers shift down by VC (static indices only, loop rolled over the groups). Entries
+// past the block only ever reach registers that are already dead.
+//   lookahead_u12: block (k, k+1) = L11^{-1} A12 in place; lane j owns COLUMN j, coef = Lt (the
+//       transposed copy of L11 that diag_lu_rot leaves).
+//   lookahead_l21: block (k+1, k) = A21 U11^{-1} in place; lane i owns ROW i, coef = U11 (the
+//       diagonal block itself), scale = rdiag.
+template <typename T, int NB, bool SCALE, typename Store>
+__device__ __forceinline__ void tri_piece(T (&a)[NB], const T* coef, int ldc, const T* scale, Store store) {
+  using V = typename VecOf<T>::type;
+  constexpr int VC = VecOf<T>::VC, NV = NB / VC;
+#pragma unroll 1
+  for (int g = 0; g < NV; ++g) {
+#pragma unroll
+    for (int s_ = 0; s_ < VC; ++s_) {
+      const int p = g * VC + s_;
+      T x = a[s_];
+      if (SCALE) x *= scale[p];
+      store(p, x);
+      const T* cr = coef + (size_t)p * ldc + g * VC;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        if (c * VC + VC - 1 <= s_) continue;
+        T t[VC];
+        vec_get<T>(*reinterpret_cast<const V*>(cr + c * VC), t);
+#pragma unroll
+        for (int q = 0; q < VC; ++q)
+          if (c * VC + q > s_) a[c * VC + q] = fma(-x, t[q], a[c * VC + q]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j + VC < NB; ++j) a[j] = a[j + VC];
+  }
+}
+
 template <typename T, int MODE, int NB>
-__device__ __noinline__ void lookahead_u12(MPtr<T, MODE> Db, int ld) {
-  const T* const D = Db.get();
+__device__ __noinline__ void lookahead_u12(MPtr<T, MODE> Db, int ld, int o_lt, int ldlt) {
   T* const B = Db.get() + NB;                     // block (k, k+1): same rows, next NB columns
+  const T* const Lt = smem_base<T>() + o_lt;
   const int lane = threadIdx.x & 31;
   const int lj = lane < NB ? lane : NB - 1;
-  // lane j owns COLUMN j: the substitution needs no cross-lane traffic at all, the entries of L11
-  // are warp-uniform (broadcast) loads that do not depend on the running values
   T a[NB];
 #pragma unroll
   for (int i = 0; i < NB; ++i) a[i] = B[(size_t)i * ld + lj];
-#pragma unroll 1
-  for (int q = 0; q < NB; ++q) {
-    const T x = a[0];                              // U12[q][j] is final
-    if (lane < NB) B[(size_t)q * ld + lj] = x;
-    // L[q + i][q], i >= 1; rows past the block only reach "don't care" registers
-    const T* lc = D + (size_t)q * ld + q;
-#pragma unroll
-    for (int i = 1; i < NB; ++i) a[i - 1] = fma(-lc[(size_t)i * ld], x, a[i]);
-  }
+  tri_piece<T, NB, false>(a, Lt, ldlt, nullptr, [&](int p, T x) { if (lane < NB) B[(size_t)p * ld + lj] = x; });
   __syncwarp();
 }
 
@@ -471,15 +518,7 @@ __device__ __noinline__ void lookahead_l21(MPtr<T, MODE> Db, int ld, int o_rdiag
     for (int q = 0; q < VC; ++q) a[c * VC + q] = t[q];
   }
   __syncwarp();                                    // all rows are in registers before any store
-#pragma unroll 1
-  for (int p = 0; p < NB; ++p) {
-    const T l = a[0] * rdiag[p];
-    if (lane < NB) row[p] = l;
-    // U[p][p + j], j >= 1; entries past the block only reach "don't care" registers
-    const T* up = D + (size_t)p * ld + p;
-#pragma unroll
-    for (int j = 1; j < NB; ++j) a[j - 1] = fma(-l, up[j], a[j]);
-  }
+  tri_piece<T, NB, true>(a, D, ld, rdiag, [&](int p, T x) { if (lane < NB) row[p] = x; });
   __syncwarp();
 }
 
@@ -558,7 +597,7 @@ __device__ __forceinline__ void lu_region(MPtr<T, MODE> Ab, int ld, int sz, int 
   const MPtr<T, 0> Lrb = Lb.plus(-(long long)sz * ldl);
   if (warp == 0) {
     const long long c0 = prof ? clock64() : 0;
-    diag_lu_rot<T, MODE, NB>(Ab, ld, o_perm_i, o_rdiag, lv.o_flag_i, lv.o_stage, 0);
+    diag_lu_rot<T, MODE, NB>(Ab, ld, o_perm_i, o_rdiag, lv.o_flag_i, lv.o_stage, lv.o_lt, lv.ldlt, 0);
     if (prof && lane == 0) { prof[11] += 1; if (*smem_int(lv.o_flag_i)) prof[10] += 1; prof[6] += clock64() - c0; }
   }
   __syncthreads();
@@ -576,14 +615,14 @@ __device__ __forceinline__ void lu_region(MPtr<T, MODE> Ab, int ld, int sz, int 
       // ---- look-ahead group: warp 0 -> U12 block, warp 1 -> L21 block (in parallel)
       const long long c0 = prof ? clock64() : 0;
       const MPtr<T, MODE> Db = Ab.plus((long long)k0 * ld + k0);
-      if (warp == 0) lookahead_u12<T, MODE, NB>(Db, ld);
+      if (warp == 0) lookahead_u12<T, MODE, NB>(Db, ld, lv.o_lt, lv.ldlt);
       else lookahead_l21<T, MODE, NB>(Db, ld, o_rdiag + k0);
       named_bar_sync(2, 64);                                     // the two pieces see each other
       if (warp == 0) {
         named_bar_arrive(1, blockDim.x);                         // release them to everyone (warp 1 syncs below)
         const long long c1 = prof ? clock64() : 0;
         diag_lu_rot<T, MODE, NB>(Ab.plus((long long)r0 * ld + r0), ld, o_perm_i + r0, o_rdiag + r0,
-                                 lv.o_flag_i + ((kb + 1) & 1), lv.o_stage, 1);
+                                 lv.o_flag_i + ((kb + 1) & 1), lv.o_stage, lv.o_lt, lv.ldlt, 1);
         if (prof && lane == 0) {
           prof[11] += 1; if (*smem_int(lv.o_flag_i + ((kb + 1) & 1))) prof[10] += 1;
           const long long c2 = clock64(); prof[12] += c1 - c0; prof[6] += c2 - c1;

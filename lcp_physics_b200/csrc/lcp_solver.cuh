@@ -21,6 +21,7 @@ struct Plan {
   int mode;                   // 0 smem, 1 split, 2 L2
   int ldT, ldL, ldG, ldQi;
   int stage_ld;               // leading dimension for staging G in T's region during pre-factor (0 = no)
+  int prefetch;               // 1: prefetch R into T's region with cp.async (0 via LCPB200_NO_PREFETCH, debugging)
   int lds;                    // leading dimension of the diagonal-block staging tile
   int G_smem, Qi_smem;
   int off_T, off_L, off_G, off_Qi, off_vec;   // shared offsets, in elements
@@ -43,6 +44,7 @@ struct Vecs {
   T *dxc, *dsc, *dzc, *dyc;
   T *rs2;
   T *qinv;                    // n: 1/diag(Q) when Q is diagonal (SceneCtx::qdiag)
+  T *lt;                      // nb*(nb+4)+nb: transposed copy of the current diagonal block's L (look-ahead)
   T *scratch;                 // max(4 nt, mp) elements
   T *red;                     // 128 elements
   int *perm;                  // mp ints
@@ -58,11 +60,11 @@ struct Vecs {
     LCPB200_TAKE(tn, n); LCPB200_TAKE(tn2, n);
     LCPB200_TAKE(dxa, n); LCPB200_TAKE(dsa, mp); LCPB200_TAKE(dza, mp); LCPB200_TAKE(dya, e);
     LCPB200_TAKE(dxc, n); LCPB200_TAKE(dsc, mp); LCPB200_TAKE(dzc, mp); LCPB200_TAKE(dyc, e);
-    LCPB200_TAKE(rs2, mp); LCPB200_TAKE(qinv, n);
+    LCPB200_TAKE(rs2, mp); LCPB200_TAKE(qinv, n); LCPB200_TAKE(lt, nb * (nb + 4) + nb);
     LCPB200_TAKE(scratch, 4 * nt > mp ? 4 * nt : mp); LCPB200_TAKE(red, 128);
     { T* pp; LCPB200_TAKE(pp, mp); perm = reinterpret_cast<int*>(pp); }
     LCPB200_TAKE(stage, 4); LCPB200_TAKE(rdiag, mp);
-    (void)nb; (void)lds;
+    (void)lds;
     { T* pp; LCPB200_TAKE(pp, 4); iflag = reinterpret_cast<int*>(pp); }
 #undef LCPB200_TAKE
     return o;
@@ -79,6 +81,7 @@ struct SceneCtx {
   T *R, *X, *XA, *S11, *Vm, *W;
   bool Rsaved;                // R points at a matrix saved by the forward pass (read-only)
   bool qdiag;                 // Q is diagonal: Q^{-1} v is an element-wise product with Vecs::qinv
+  bool t_prefetched;          // R is already on its way into T's shared region (prefetch_T)
   int stage_ld;               // > 0: G may be staged in T's shared region with this leading dimension
   const T* Gsrc;              // this scene's G in global memory
   int* lu_flag;
@@ -317,6 +320,42 @@ __device__ __noinline__ bool prefactor(SceneCtx<T, MODE>& c, int* flag) {
   return true;
 }
 
+// ------------------------------------------------------------------ prefetch of R for the next factor_kkt
+// Only the diagonal of T = R + diag(1/d) changes between iterations but the LU overwrites T, so R
+// is re-read every iteration. Once the corrector solve is done the old factors are dead: the copy
+// R -> T's shared region is issued there with cp.async and completes behind the step-length /
+// residual phases; factor_kkt then only adds the diagonal.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <typename T, int MODE>
+__device__ __forceinline__ void prefetch_T(SceneCtx<T, MODE>& c) {
+  constexpr int VC = VecOf<T>::VC;
+  if (MODE == 2) return;
+  const int m = c.m, m1 = c.tv.m1, mp = c.mp, tid = threadIdx.x, NT = blockDim.x;
+  if ((m % VC) != 0 || (reinterpret_cast<uintptr_t>(c.R) & 15) != 0) return;
+  T* const tmain = c.tv.main();
+  T* const tlow = (MODE == 1) ? c.tv.low() : tmain;
+  const int mv = m / VC;                          // vectors per row of R
+  const int r1 = min(m1, m);
+  for (int t = tid; t < r1 * mv; t += NT) {       // main rows [0, m1) x columns [0, m)
+    const int i = t / mv, j = (t - i * mv) * VC;
+    cp_async16(tmain + (size_t)i * c.tv.ld + j, c.R + (size_t)i * m + j);
+  }
+  if (MODE == 1) {                                // low rows [m1, m) x columns [0, m1)
+    const int m1v = m1 / VC;
+    for (int t = tid; t < (m - m1) * m1v; t += NT) {
+      const int i = m1 + t / m1v, j = (t % m1v) * VC;
+      cp_async16(tlow + (size_t)(i - m1) * c.tv.ldl + j, c.R + (size_t)i * m + j);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  c.t_prefetched = true;
+}
+
 // ------------------------------------------------------------------ factor_kkt (pdipm.py:414-454)
 // T = R + diag(1/d) (:427-429), padded with an identity block, loaded into the view, then LU (:431).
 template <typename T, int MODE>
@@ -332,7 +371,28 @@ __device__ __noinline__ void factor_kkt(SceneCtx<T, MODE>& c) {
   for (int i = tid; i < mp; i += NT) dinv[i] = i < m ? T(1) / d[i] : T(1);
   __syncthreads();
   const bool vec_ok = (m % VC == 0) && ((reinterpret_cast<uintptr_t>(c.R) & 15) == 0);
-  if (vec_ok) {
+  if (c.t_prefetched) {
+    // R is arriving by cp.async (prefetch_T): finish it, fill the padding, add the diagonal
+    c.t_prefetched = false;
+    cp_async_wait_all();
+    const int mv = mp / VC;
+    if (mp != m) {
+      T z[VC];
+#pragma unroll
+      for (int q = 0; q < VC; ++q) z[q] = 0;
+      for (int t = tid; t < m1 * mv; t += NT) {
+        const int i = t / mv, j = (t - i * mv) * VC;
+        if (!(i < m && j < m)) *reinterpret_cast<V*>(tmain + (size_t)i * c.tv.ld + j) = vec_make(z);
+      }
+      const int m1v = m1 / VC;
+      for (int t = tid; t < (mp - m1) * m1v; t += NT) {
+        const int i = m1 + t / m1v, j = (t % m1v) * VC;
+        if (!(i < m && j < m)) *reinterpret_cast<V*>(tlow + (size_t)(i - m1) * c.tv.ldl + j) = vec_make(z);
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < m1; i += NT) tmain[(size_t)i * c.tv.ld + i] += dinv[i];
+  } else if (vec_ok) {
     const int mv = mp / VC;
     constexpr int UB = 8;                          // independent L2 loads in flight per thread
     // main rows [0,m1) x all columns
@@ -404,6 +464,7 @@ __device__ __noinline__ void factor_kkt(SceneCtx<T, MODE>& c) {
   lv.o_rdiag = (int)(v.rdiag - smem_base<T>());
   lv.o_stage = (int)(v.red - smem_base<T>());   // 2 x (NB + VC) elements of the (idle) reduction buffer
   lv.lds = c.lds;
+  lv.o_lt = (int)(v.lt - smem_base<T>()); lv.ldlt = Blk<T>::NB + 4;
   lu_factor_view<T, MODE>(c.tv, c.R + (size_t)m1 * m + m1, m, (int)(dinv - smem_base<T>()), m, lv, c.prof);
   prof_lap(c, PH_LU);
 }
@@ -509,7 +570,7 @@ __device__ void setup_ctx(SceneCtx<T, MODE>& c, const Plan& P, T* sm, T* ws, int
   c.tv.u12 = ws + P.w_U12;
   c.R = ws + P.w_R; c.X = ws + P.w_X; c.XA = ws + P.w_XA; c.S11 = ws + P.w_S11;
   c.Vm = ws + P.w_V; c.W = ws + P.w_W;
-  c.Rsaved = false; c.qdiag = false; c.stage_ld = P.stage_ld; c.Gsrc = nullptr;
+  c.Rsaved = false; c.qdiag = false; c.t_prefetched = false; c.stage_ld = P.stage_ld; c.Gsrc = nullptr;
   c.lu_flag = lu_flag;
   c.prof = prof ? prof + (size_t)blockIdx.x * PH_COUNT : nullptr;
   Vecs<T> v = c.vecs();
@@ -606,7 +667,12 @@ __global__ void __launch_bounds__(512, 1) lcp_forward_kernel(const FwdArgs<T> a)
       // ---- residuals                                              :82-96
       gemv_cols_v(c.G, c.ldG, m, n, v.z, v.scratch, [&](int j, T acc) { v.rx[j] = acc; });
       if (e > 0) gemv_cols_v(c.A, n, e, n, v.y, v.scratch, [&](int j, T acc) { v.rx[j] = acc + v.rx[j]; });
-      gemv_rows_v(c.Q, n, n, n, v.x, [&](int i, T acc) { v.rx[i] = v.rx[i] + acc + p[i]; });
+      if (c.qdiag) {
+        for (int i = tid; i < n; i += NT) v.rx[i] = v.rx[i] + c.Q[(size_t)i * n + i] * v.x[i] + p[i];
+        __syncthreads();
+      } else {
+        gemv_rows_v(c.Q, n, n, n, v.x, [&](int i, T acc) { v.rx[i] = v.rx[i] + acc + p[i]; });
+      }
       gemv_rows_v(c.G, c.ldG, m, n, v.x, [&](int i, T acc) { v.rz[i] = acc + v.s[i] - h[i]; });
       gemv_rows_v(c.F, m, m, m, v.z, [&](int i, T acc) { v.rz[i] -= acc; });
       if (e > 0) gemv_rows_v(c.A, n, e, n, v.x, [&](int i, T acc) { v.ry[i] = acc - b[i]; });
@@ -654,6 +720,7 @@ __global__ void __launch_bounds__(512, 1) lcp_forward_kernel(const FwdArgs<T> a)
       __syncthreads();
       prof_lap(c, PH_STEP);
       solve_kkt(c, -1, off(v.rs2), -1, -1, off(v.dxc), off(v.dsc), off(v.dzc), off(v.dyc));
+      if (it + 1 < a.max_iter && P.prefetch) prefetch_T(c);                     // the factors are dead from here on
       prof_lap(c, PH_SOLVE);
       for (int i = tid; i < n; i += NT) v.dxa[i] += v.dxc[i];    // :160-163
       for (int i = tid; i < m; i += NT) { v.dsa[i] += v.dsc[i]; v.dza[i] += v.dzc[i]; }
@@ -667,6 +734,7 @@ __global__ void __launch_bounds__(512, 1) lcp_forward_kernel(const FwdArgs<T> a)
       __syncthreads();
       prof_lap(c, PH_STEP);
     }
+    if (c.t_prefetched) { cp_async_wait_all(); c.t_prefetched = false; }   // early exit: drain before T's region is reused
     if (tid == 0) { a.status[sc] = status; a.iters[sc] = it; if (a.resid) a.resid[sc] = best; }
     __syncthreads();
   }

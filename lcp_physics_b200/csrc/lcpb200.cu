@@ -99,6 +99,7 @@ static int make_plan(lcpb200_handle_s* h) {
     }
   }
   P.stage_ld = 0;
+  P.prefetch = getenv("LCPB200_NO_PREFETCH") ? 0 : 1;
   if (P.mode != 2) {
     const int lds = pad_ld(n, w);
     if ((long long)m * lds <= (long long)P.m1 * P.ldT) P.stage_ld = lds;

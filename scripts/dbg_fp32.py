@@ -17,3 +17,4 @@ idx = torch.argsort(err, descending=True)[:8]
 for i in idx.tolist():
     print("scene %2d err %.3e own %.3e mine %.3e" % (i, err[i], own[i], mine[i]))
 print("within 1e-3: %.3f" % (err < 1e-3).float().mean())
+print("median err %.3e own %.3e mine %.3e | p90 err %.3e own %.3e mine %.3e" % (err.median(), own.median(), mine.median(), err.quantile(0.9), own.quantile(0.9), mine.quantile(0.9)))
