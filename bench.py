@@ -34,6 +34,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+if os.environ.get("OMP_NUM_THREADS") == "1" and "TORCHELASTIC_RUN_ID" in os.environ:
+    del os.environ["OMP_NUM_THREADS"]      # torchrun's per-rank default; see use_all_host_threads()
 import torch  # noqa: E402
 
 NB, NC, FD, NEQ = 32, 64, 2, 0
@@ -103,6 +105,18 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+WORKLOAD = ("LCPFunction fwd+bwd (all 7 gradients), batch=%d scenes/GPU x 64 contacts x 2 fric dirs "
+            "(n=96, m=256, neq=0), fp32, max_iter=10, pile scenes (lcp_physics_b200/scenes.py)")
+
+
+def use_all_host_threads():
+    """Threads the CPU legs run with. torchrun exports OMP_NUM_THREADS=1 for every rank; that default is
+    dropped at the top of this file (before torch is imported) so that the CPU legs get torch's own
+    default = all host cores, exactly as in a plain `python bench.py` run. (Calling
+    torch.set_num_threads() after import instead dead-locked MKL's threaded SLASWP in this image.)"""
+    return torch.get_num_threads()
+
+
 def cpu_reference_leg(B_sample, dtype, seed, reps=1):
     """Oracle port of the reference CPU path (as-is semantics), fwd+bwd on B_sample scenes."""
     from oracle import pdipm_oracle as po
@@ -122,7 +136,7 @@ def cpu_reference_leg(B_sample, dtype, seed, reps=1):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cores = torch.get_num_threads()
+    cores = use_all_host_threads()
     Bs = args.ref_batch
     for _ in range(args.warmup and 1):
         cpu_reference_leg(8, torch.float32, 1)
@@ -135,8 +149,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "LCPFunction fwd+bwd, 64 contacts x 2 fric dirs (n=96, m=256), fp32, max_iter=10",
-                   "sample_batch": Bs},
+        "config": {"workload": WORKLOAD % args.batch, "global_batch": world * args.batch,
+                   "parallelism": "host CPU, rank 0 only", "sample_batch": Bs,
+                   "note": "each step times a bounded sample of the workload (sample_batch scenes) on the host cores"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d scenes per step (of the 4096-scene batch), fwd+bwd, as-is reference "
                                    "semantics incl. util.py:86-90 pivot loop" % Bs},
@@ -262,8 +277,7 @@ def run_b200(args, rank, world, local_rank):
         "metric": METRIC, "value": world * B * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "LCPFunction fwd+bwd (all 7 gradients), batch=%d scenes/GPU x 64 contacts x 2 fric "
-                               "dirs (n=96, m=256, neq=0), fp32, max_iter=10, pile scenes (lcp_physics_b200/scenes.py)" % B,
+        "config": {"workload": WORKLOAD % B,
                    "global_batch": world * B, "parallelism": "scene-sharded x%d" % world,
                    "l2": "inputs+gradients per step (3.3 GB) exceed the 126 MB L2, no flush needed",
                    "mean_pdipm_iters": iters_mean, "parity_ok": ok},
@@ -286,8 +300,9 @@ def run_b200(args, rank, world, local_rank):
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
+        ncores = use_all_host_threads()
         val, dt = cpu_reference_leg(args.cpu_sample, dtype, 7)
-        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": ncores, "kind": "port",
                                 "sample": "%d of the 4096 scenes, fwd+bwd, %.1f s, as-is reference semantics "
                                           "(incl. util.py:86-90 pivot loop)" % (args.cpu_sample, dt)}
     print(json.dumps(line), flush=True)
