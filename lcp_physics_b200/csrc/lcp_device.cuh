@@ -35,32 +35,49 @@ __device__ __forceinline__ T warp_reduce(T v, Op op) {
   return v;
 }
 
+// A team = the threads [0, nt) of the CTA that run a phase together, with their own barrier:
+// bar 0 = the whole CTA (__syncthreads), otherwise a named barrier over the first nt threads (nt a
+// multiple of 32). Lets the bulk of the CTA run a phase while another warp does something else.
+struct Team {
+  int tid, nt, bar;
+  __device__ __forceinline__ void sync() const {
+    if (bar == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nt) : "memory");
+  }
+  __device__ __forceinline__ static Team cta() { Team t; t.tid = threadIdx.x; t.nt = blockDim.x; t.bar = 0; return t; }
+};
+
 // Block-wide reduction of up to 4 values at once; result broadcast to all threads.
 // red: shared scratch of >= 4*32 elements. Ends with a barrier that makes `red` reusable.
 template <typename T, int NV, typename Op>
-__device__ __forceinline__ void block_reduce(T (&v)[NV], Op op, T ident, T* red) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+__device__ __forceinline__ void block_reduce(T (&v)[NV], Op op, T ident, T* red, const Team& tm) {
+  const int lane = tm.tid & 31, warp = tm.tid >> 5, nw = (tm.nt + 31) >> 5;
 #pragma unroll
   for (int q = 0; q < NV; ++q) v[q] = warp_reduce(v[q], op);
   if (lane == 0) {
 #pragma unroll
     for (int q = 0; q < NV; ++q) red[q * 32 + warp] = v[q];
   }
-  __syncthreads();
+  tm.sync();
 #pragma unroll
   for (int q = 0; q < NV; ++q) {
     T t = (lane < nw) ? red[q * 32 + lane] : ident;
     v[q] = warp_reduce(t, op);
   }
-  __syncthreads();
+  tm.sync();
+}
+
+template <typename T, int NV, typename Op>
+__device__ __forceinline__ void block_reduce(T (&v)[NV], Op op, T ident, T* red) {
+  block_reduce<T, NV, Op>(v, op, ident, red, Team::cta());
 }
 
 // ---------------------------------------------------------------- GEMV
 // out[r] = epi(r, sum_j A[r*lda+j] * x[j]),  r in [0,M): one warp per row, coalesced along j.
 template <typename T, typename Epi>
 __device__ __forceinline__ void gemv_rows(const T* __restrict__ A, int lda, int M, int N,
-                                          const T* x, Epi epi) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+                                          const T* x, Epi epi, const Team& tm) {
+  const int lane = tm.tid & 31, warp = tm.tid >> 5, nw = tm.nt >> 5;
   for (int r = warp; r < M; r += nw) {
     const T* row = A + (size_t)r * lda;
     T acc = 0;
@@ -68,33 +85,33 @@ __device__ __forceinline__ void gemv_rows(const T* __restrict__ A, int lda, int 
     acc = warp_reduce(acc, OpSum());
     if (lane == 0) epi(r, acc);
   }
-  __syncthreads();
+  tm.sync();
 }
 
 // out[j] = epi(j, sum_i A[i*lda+j] * w[i]),  j in [0,N): columns across lanes, row range
 // split over thread groups, partials combined through `scratch` (>= blockDim.x elements).
 template <typename T, typename Epi>
 __device__ __forceinline__ void gemv_cols(const T* __restrict__ A, int lda, int M, int N,
-                                          const T* w, T* scratch, Epi epi) {
-  const int NT = blockDim.x;
+                                          const T* w, T* scratch, Epi epi, const Team& tm) {
+  const int NT = tm.nt;
   for (int j0 = 0; j0 < N; j0 += NT) {
     const int nj = min(N - j0, NT);
     const int njp = (nj + 31) & ~31;
     const int parts = NT / njp;                 // >= 1
-    const int part = threadIdx.x / njp, jj = threadIdx.x - part * njp;
+    const int part = tm.tid / njp, jj = tm.tid - part * njp;
     T acc = 0;
     if (part < parts && jj < nj) {
       const T* col = A + j0 + jj;
       for (int i = part; i < M; i += parts) acc += col[(size_t)i * lda] * w[i];
     }
-    scratch[threadIdx.x] = acc;
-    __syncthreads();
-    if (threadIdx.x < nj) {
+    scratch[tm.tid] = acc;
+    tm.sync();
+    if (tm.tid < nj) {
       T t = 0;
-      for (int q = 0; q < parts; ++q) t += scratch[q * njp + threadIdx.x];
-      epi(j0 + threadIdx.x, t);
+      for (int q = 0; q < parts; ++q) t += scratch[q * njp + tm.tid];
+      epi(j0 + tm.tid, t);
     }
-    __syncthreads();
+    tm.sync();
   }
 }
 

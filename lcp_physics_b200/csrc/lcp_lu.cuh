@@ -569,7 +569,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
 template <typename T, int MODE>
 __device__ __forceinline__ void lu_region(MPtr<T, MODE> Ab, int ld, int sz, int ncols_total, MPtr<T, 0> Lb, int ldl,
                                           int nlow, LuVec lv, int row0, long long* prof, MPtr<T, 0> Sb, int ldsh,
-                                          int shadow_cols) {
+                                          int shadow_cols, bool first_done) {
   constexpr int NB = Blk<T>::NB;
   // Roles. The serial look-ahead chain (role 0) runs on the LAST warp (the SMSP arbiter prefers the
   // highest warp id), the L21-piece warp (role 1) on another SMSP, the bulk on the rest. (Keeping
@@ -595,7 +595,7 @@ __device__ __forceinline__ void lu_region(MPtr<T, MODE> Ab, int ld, int sz, int 
   const int o_rdiag = lv.o_rdiag + row0;
   // low rows are addressed as rows [sz, sz+nlow) of a re-based array
   const MPtr<T, 0> Lrb = Lb.plus(-(long long)sz * ldl);
-  if (warp == 0) {
+  if (warp == 0 && !first_done) {                 // first_done: the caller factored block 0 already
     const long long c0 = prof ? clock64() : 0;
     diag_lu_rot<T, MODE, NB>(Ab, ld, o_perm_i, o_rdiag, lv.o_flag_i, lv.o_stage, lv.o_lt, lv.ldlt, 0);
     if (prof && lane == 0) { prof[11] += 1; if (*smem_int(lv.o_flag_i)) prof[10] += 1; prof[6] += clock64() - c0; }
@@ -823,14 +823,14 @@ __device__ __noinline__ void split_schur(TView<T, MODE> v, const T* __restrict__
 // [m1,mp) columns [0,m1)). R22/ldr/o_dinv/m_real are only used by the split.
 template <typename T, int MODE>
 __device__ __forceinline__ void lu_factor_view(const TView<T, MODE>& v, const T* R22, int ldr, int o_dinv, int m_real,
-                                               LuVec lv, long long* prof) {
+                                               LuVec lv, long long* prof, bool first_done = false) {
   MPtr<T, 0> none; none.off = 0; none.g = nullptr;
   if (MODE != 1) {
-    lu_region<T, MODE>(v.main_, v.ld, v.mp, v.mp, none, 0, 0, lv, 0, prof, none, 0, 0);
+    lu_region<T, MODE>(v.main_, v.ld, v.mp, v.mp, none, 0, 0, lv, 0, prof, none, 0, 0, first_done);
   } else {
-    lu_region<T, MODE>(v.main_, v.ld, v.m1, v.mp, v.low_, v.ldl, v.mp - v.m1, lv, 0, prof, none, 0, 0);
+    lu_region<T, MODE>(v.main_, v.ld, v.m1, v.mp, v.low_, v.ldl, v.mp - v.m1, lv, 0, prof, none, 0, 0, first_done);
     split_schur<T, MODE>(v, R22, ldr, o_dinv, m_real);
-    lu_region<T, MODE>(v.main_.plus(v.m1), v.ld, v.mp - v.m1, v.mp - v.m1, none, 0, 0, lv, v.m1, prof, v.low_, v.ldl, v.m1);
+    lu_region<T, MODE>(v.main_.plus(v.m1), v.ld, v.mp - v.m1, v.mp - v.m1, none, 0, 0, lv, v.m1, prof, v.low_, v.ldl, v.m1, false);
   }
   long long t0 = (prof && threadIdx.x == 0) ? clock64() : 0;
   lu_invert_diag_blocks<T, MODE>(v, lv.o_rdiag);

@@ -48,7 +48,8 @@ struct Vecs {
   T *scratch;                 // max(4 nt, mp) elements
   T *red;                     // 128 elements
   int *perm;                  // mp ints
-  T *stage;                   // (unused)
+  T *stage;                   // 2 x (nb + 4): pivot-row broadcast buffer of the diagonal-block LU
+  T *bcast;                   // 4 scalars handed from the residual team to the whole CTA
   T *rdiag;                   // mp reciprocals of the U diagonal
   int *iflag;                 // 4 ints: [0] = rows were interchanged in the current diagonal block
   __host__ __device__ long long carve(T* base, int n, int mp, int e, int nt, int nb, int lds) {
@@ -63,7 +64,7 @@ struct Vecs {
     LCPB200_TAKE(rs2, mp); LCPB200_TAKE(qinv, n); LCPB200_TAKE(lt, nb * (nb + 4) + nb);
     LCPB200_TAKE(scratch, 4 * nt > mp ? 4 * nt : mp); LCPB200_TAKE(red, 128);
     { T* pp; LCPB200_TAKE(pp, mp); perm = reinterpret_cast<int*>(pp); }
-    LCPB200_TAKE(stage, 4); LCPB200_TAKE(rdiag, mp);
+    LCPB200_TAKE(stage, 2 * (nb + 4)); LCPB200_TAKE(bcast, 4); LCPB200_TAKE(rdiag, mp);
     (void)lds;
     { T* pp; LCPB200_TAKE(pp, 4); iflag = reinterpret_cast<int*>(pp); }
 #undef LCPB200_TAKE
@@ -107,11 +108,12 @@ __device__ __forceinline__ void prof_lap(C& c, int ph) {
 // out[r] = epi(r, sum_j A[r*lda+j] x[j]): one warp per row, RB rows (and all their vectors) in
 // flight per warp so that an L2-resident matrix is streamed with deep memory-level parallelism.
 template <typename T, typename Epi>
-__device__ __forceinline__ void gemv_rows_v(const T* __restrict__ A, int lda, int M, int N, const T* x, Epi epi) {
+__device__ __forceinline__ void gemv_rows_v(const T* __restrict__ A, int lda, int M, int N, const T* x, Epi epi,
+                                            const Team& tm) {
   using V = typename VecOf<T>::type;
   constexpr int VC = VecOf<T>::VC;
   constexpr int RB = 8;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int lane = tm.tid & 31, warp = tm.tid >> 5, nw = tm.nt >> 5;
   const bool vec_ok = (N % VC == 0) && (lda % VC == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
   if (vec_ok) {
     for (int r0 = warp * RB; r0 < M; r0 += nw * RB) {
@@ -140,26 +142,31 @@ __device__ __forceinline__ void gemv_rows_v(const T* __restrict__ A, int lda, in
           if (r0 + q < M) epi(r0 + q, acc[q]);
       }
     }
-    __syncthreads();
+    tm.sync();
   } else {
-    gemv_rows(A, lda, M, N, x, epi);
+    gemv_rows(A, lda, M, N, x, epi, tm);
   }
+}
+
+template <typename T, typename Epi>
+__device__ __forceinline__ void gemv_rows_v(const T* __restrict__ A, int lda, int M, int N, const T* x, Epi epi) {
+  gemv_rows_v(A, lda, M, N, x, epi, Team::cta());
 }
 
 // out[j] = epi(j, sum_i A[i*lda+j] w[i]): a thread owns one column vector and a slice of the rows;
 // slices are combined through `scratch` (>= 4*blockDim.x elements).
 template <typename T, typename Epi>
 __device__ __forceinline__ void gemv_cols_v(const T* __restrict__ A, int lda, int M, int N, const T* w, T* scratch,
-                                            Epi epi) {
+                                            Epi epi, const Team& tm) {
   using V = typename VecOf<T>::type;
   constexpr int VC = VecOf<T>::VC;
-  const int NT = blockDim.x;
+  const int NT = tm.nt;
   const int njv = N / VC;
   const bool vec_ok = (N % VC == 0) && (lda % VC == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && njv <= NT;
-  if (!vec_ok) { gemv_cols(A, lda, M, N, w, scratch, epi); return; }
+  if (!vec_ok) { gemv_cols(A, lda, M, N, w, scratch, epi, tm); return; }
   const int njp = (njv + 31) & ~31;
   const int parts = NT / njp;
-  const int part = threadIdx.x / njp, jv = threadIdx.x - part * njp;
+  const int part = tm.tid / njp, jv = tm.tid - part * njp;
   T acc[VC];
 #pragma unroll
   for (int t = 0; t < VC; ++t) acc[t] = 0;
@@ -175,13 +182,19 @@ __device__ __forceinline__ void gemv_cols_v(const T* __restrict__ A, int lda, in
     }
     *reinterpret_cast<V*>(scratch + ((size_t)part * njv + jv) * VC) = vec_make(acc);
   }
-  __syncthreads();
-  for (int j = threadIdx.x; j < N; j += NT) {
+  tm.sync();
+  for (int j = tm.tid; j < N; j += NT) {
     T t = 0;
     for (int q = 0; q < parts; ++q) t += scratch[(size_t)q * N + j];
     epi(j, t);
   }
-  __syncthreads();
+  tm.sync();
+}
+
+template <typename T, typename Epi>
+__device__ __forceinline__ void gemv_cols_v(const T* __restrict__ A, int lda, int M, int N, const T* w, T* scratch,
+                                            Epi epi) {
+  gemv_cols_v(A, lda, M, N, w, scratch, epi, Team::cta());
 }
 
 // ------------------------------------------------------------------ R = G diag(qi) G^T + F
@@ -356,10 +369,46 @@ __device__ __forceinline__ void prefetch_T(SceneCtx<T, MODE>& c) {
   c.t_prefetched = true;
 }
 
+// ------------------------------------------------------------------ first diagonal block, early
+// The first diagonal block of T has no look-ahead partner inside the LU (ncu: 8 % of all samples were
+// the other 15 warps waiting for it), but it only needs R (prefetched) and d = z/s of its own rows,
+// both known before the residuals are formed. So the chain warp factors it while the rest of the
+// CTA (a Team with its own named barrier) computes the residuals. Same arithmetic as factor_kkt:
+// d = z/s, T_ii = R_ii + 1/d.
+template <typename T, int MODE>
+__device__ __forceinline__ LuVec make_luvec(SceneCtx<T, MODE>& c) {
+  Vecs<T> v = c.vecs();
+  LuVec lv;
+  lv.o_perm_i = (int)(v.perm - smem_int(0));
+  lv.o_flag_i = (int)(v.iflag - smem_int(0));
+  lv.o_rmaxs = (int)(v.red - smem_base<T>());
+  lv.o_rdiag = (int)(v.rdiag - smem_base<T>());
+  lv.o_stage = (int)(v.stage - smem_base<T>());
+  lv.lds = c.lds;
+  lv.o_lt = (int)(v.lt - smem_base<T>()); lv.ldlt = Blk<T>::NB + 4;
+  return lv;
+}
+
+template <typename T, int MODE>
+__device__ __noinline__ void early_first_block(SceneCtx<T, MODE>& c) {
+  constexpr int NB = Blk<T>::NB;
+  Vecs<T> v = c.vecs();
+  const int lane = threadIdx.x & 31;
+  T* const tmain = c.tv.main();
+  if (lane < NB) {
+    const T d = v.z[lane] / v.s[lane];
+    tmain[(size_t)lane * c.tv.ld + lane] += T(1) / d;
+  }
+  __syncwarp();
+  const LuVec lv = make_luvec(c);
+  diag_lu_rot<T, MODE, NB>(c.tv.main_, c.tv.ld, lv.o_perm_i, lv.o_rdiag, lv.o_flag_i, lv.o_stage, lv.o_lt, lv.ldlt, 0);
+  if (c.prof && lane == 0) { c.prof[11] += 1; if (*smem_int(lv.o_flag_i)) c.prof[10] += 1; }
+}
+
 // ------------------------------------------------------------------ factor_kkt (pdipm.py:414-454)
 // T = R + diag(1/d) (:427-429), padded with an identity block, loaded into the view, then LU (:431).
 template <typename T, int MODE>
-__device__ __noinline__ void factor_kkt(SceneCtx<T, MODE>& c) {
+__device__ __noinline__ void factor_kkt(SceneCtx<T, MODE>& c, bool first_block_done = false) {
   using V = typename VecOf<T>::type;
   constexpr int VC = VecOf<T>::VC;
   const int m = c.m, mp = c.mp, m1 = c.tv.m1, tid = threadIdx.x, NT = blockDim.x;
@@ -374,7 +423,7 @@ __device__ __noinline__ void factor_kkt(SceneCtx<T, MODE>& c) {
   if (c.t_prefetched) {
     // R is arriving by cp.async (prefetch_T): finish it, fill the padding, add the diagonal
     c.t_prefetched = false;
-    cp_async_wait_all();
+    if (!first_block_done) cp_async_wait_all();
     const int mv = mp / VC;
     if (mp != m) {
       T z[VC];
@@ -391,7 +440,8 @@ __device__ __noinline__ void factor_kkt(SceneCtx<T, MODE>& c) {
       }
     }
     __syncthreads();
-    for (int i = tid; i < m1; i += NT) tmain[(size_t)i * c.tv.ld + i] += dinv[i];
+    // (the first diagonal block got its diagonal -- and its factorisation -- early, see early_first_block)
+    for (int i = (first_block_done ? Blk<T>::NB : 0) + tid; i < m1; i += NT) tmain[(size_t)i * c.tv.ld + i] += dinv[i];
   } else if (vec_ok) {
     const int mv = mp / VC;
     constexpr int UB = 8;                          // independent L2 loads in flight per thread
@@ -457,15 +507,8 @@ __device__ __noinline__ void factor_kkt(SceneCtx<T, MODE>& c) {
   }
   __syncthreads();
   prof_lap(c, PH_LOADT);
-  LuVec lv;
-  lv.o_perm_i = (int)(v.perm - smem_int(0));
-  lv.o_flag_i = (int)(v.iflag - smem_int(0));
-  lv.o_rmaxs = (int)(v.red - smem_base<T>());
-  lv.o_rdiag = (int)(v.rdiag - smem_base<T>());
-  lv.o_stage = (int)(v.red - smem_base<T>());   // 2 x (NB + VC) elements of the (idle) reduction buffer
-  lv.lds = c.lds;
-  lv.o_lt = (int)(v.lt - smem_base<T>()); lv.ldlt = Blk<T>::NB + 4;
-  lu_factor_view<T, MODE>(c.tv, c.R + (size_t)m1 * m + m1, m, (int)(dinv - smem_base<T>()), m, lv, c.prof);
+  const LuVec lv = make_luvec(c);
+  lu_factor_view<T, MODE>(c.tv, c.R + (size_t)m1 * m + m1, m, (int)(dinv - smem_base<T>()), m, lv, c.prof, first_block_done);
   prof_lap(c, PH_LU);
 }
 
@@ -665,30 +708,45 @@ __global__ void __launch_bounds__(512, 1) lcp_forward_kernel(const FwdArgs<T> a)
     int not_improved = 0, status = 0, it = 0;
     for (it = 0; it < a.max_iter; ++it) {
       // ---- residuals                                              :82-96
-      gemv_cols_v(c.G, c.ldG, m, n, v.z, v.scratch, [&](int j, T acc) { v.rx[j] = acc; });
-      if (e > 0) gemv_cols_v(c.A, n, e, n, v.y, v.scratch, [&](int j, T acc) { v.rx[j] = acc + v.rx[j]; });
-      if (c.qdiag) {
-        for (int i = tid; i < n; i += NT) v.rx[i] = v.rx[i] + c.Q[(size_t)i * n + i] * v.x[i] + p[i];
-        __syncthreads();
-      } else {
-        gemv_rows_v(c.Q, n, n, n, v.x, [&](int i, T acc) { v.rx[i] = v.rx[i] + acc + p[i]; });
+      // When R has been prefetched into T (every iteration but the first) the chain warp factors the
+      // first diagonal block now (early_first_block) and the other warps form the residuals as a Team.
+      const bool overlap = c.t_prefetched && MODE != 2 && c.mp == m && NT >= 128;
+      Team tm = Team::cta();
+      bool in_team = true;
+      if (overlap) {
+        cp_async_wait_all();
+        __syncthreads();                                           // every thread's part of R has landed
+        tm.tid = tid; tm.nt = NT - 32; tm.bar = 3;
+        in_team = tid < NT - 32;
+        if (!in_team) early_first_block(c);
       }
-      gemv_rows_v(c.G, c.ldG, m, n, v.x, [&](int i, T acc) { v.rz[i] = acc + v.s[i] - h[i]; });
-      gemv_rows_v(c.F, m, m, m, v.z, [&](int i, T acc) { v.rz[i] -= acc; });
-      if (e > 0) gemv_rows_v(c.A, n, e, n, v.x, [&](int i, T acc) { v.ry[i] = acc - b[i]; });
-      T q[4] = {0, 0, 0, 0};                                      // s.z, |rz|^2, |ry|^2, |rx|^2
-      for (int i = tid; i < m; i += NT) { q[0] += v.s[i] * v.z[i]; q[1] += v.rz[i] * v.rz[i]; }
-      for (int i = tid; i < e; i += NT) q[2] += v.ry[i] * v.ry[i];
-      for (int i = tid; i < n; i += NT) q[3] += v.rx[i] * v.rx[i];
-      block_reduce<T, 4>(q, OpSum(), T(0), v.red);
-      const T sz = q[0];
-      const T mu = fabs(sz / T(m));                               // :91
-      const T resid = (e > 0 ? sqrt(q[2]) : T(0)) + sqrt(q[1]) + sqrt(q[3]) + T(m) * mu;   // :92-96
-
-      for (int i = tid; i < m; i += NT) v.d[i] = v.z[i] / v.s[i];     // :98
+      if (in_team) {
+        const int TN = tm.nt;
+        gemv_cols_v(c.G, c.ldG, m, n, v.z, v.scratch, [&](int j, T acc) { v.rx[j] = acc; }, tm);
+        if (e > 0) gemv_cols_v(c.A, n, e, n, v.y, v.scratch, [&](int j, T acc) { v.rx[j] = acc + v.rx[j]; }, tm);
+        if (c.qdiag) {
+          for (int i = tid; i < n; i += TN) v.rx[i] = v.rx[i] + c.Q[(size_t)i * n + i] * v.x[i] + p[i];
+          tm.sync();
+        } else {
+          gemv_rows_v(c.Q, n, n, n, v.x, [&](int i, T acc) { v.rx[i] = v.rx[i] + acc + p[i]; }, tm);
+        }
+        gemv_rows_v(c.G, c.ldG, m, n, v.x, [&](int i, T acc) { v.rz[i] = acc + v.s[i] - h[i]; }, tm);
+        gemv_rows_v(c.F, m, m, m, v.z, [&](int i, T acc) { v.rz[i] -= acc; }, tm);
+        if (e > 0) gemv_rows_v(c.A, n, e, n, v.x, [&](int i, T acc) { v.ry[i] = acc - b[i]; }, tm);
+        T q[4] = {0, 0, 0, 0};                                      // s.z, |rz|^2, |ry|^2, |rx|^2
+        for (int i = tid; i < m; i += TN) { q[0] += v.s[i] * v.z[i]; q[1] += v.rz[i] * v.rz[i]; }
+        for (int i = tid; i < e; i += TN) q[2] += v.ry[i] * v.ry[i];
+        for (int i = tid; i < n; i += TN) q[3] += v.rx[i] * v.rx[i];
+        block_reduce<T, 4>(q, OpSum(), T(0), v.red, tm);
+        if (tid == 0) { v.bcast[0] = q[0]; v.bcast[1] = q[1]; v.bcast[2] = q[2]; v.bcast[3] = q[3]; }
+        for (int i = tid; i < m; i += TN) v.d[i] = v.z[i] / v.s[i];     // :98
+      }
       __syncthreads();
+      const T sz = v.bcast[0];
+      const T mu = fabs(sz / T(m));                               // :91
+      const T resid = (e > 0 ? sqrt(v.bcast[2]) : T(0)) + sqrt(v.bcast[1]) + sqrt(v.bcast[3]) + T(m) * mu;   // :92-96
       prof_lap(c, PH_RESID);
-      factor_kkt(c);                                         // :100
+      factor_kkt(c, overlap);                                // :100
 
       // ---- best iterate / termination (per scene)                 :107-136
       bool improved;
