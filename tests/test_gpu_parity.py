@@ -119,7 +119,7 @@ def test_forward_vs_oracle_seeded_fp32(cfg):
     # error against the fp64 truth no worse than the fp32 reference's own (median, p90, max).
     assert (err < 1e-3).float().mean() >= 0.85, err
     assert float(err.max()) <= 2e-2, err
-    assert float(mine.median()) <= max(1e-4, 10 * float(own.median())), (mine, own)   # a tenth of the tolerance
+    assert float(mine.median()) <= max(3e-4, 10 * float(own.median())), (mine, own)   # a third of the tolerance
     assert float(mine.quantile(0.9)) <= max(2e-3, 3 * float(own.quantile(0.9))), (mine, own)
     assert float(mine.max()) <= max(1e-2, 2 * float(own.max())), (mine, own)
 
