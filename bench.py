@@ -296,7 +296,7 @@ def run_b200(args, rank, world, local_rank):
                      "resident_bytes_gbs": alg["b_fwd_resident"] * B / (fwd_ms * 1e-3) / 1e9,
                      "fma": {"achieved_tflops": alg["W_fwd"] * B / (fwd_ms * 1e-3) / 1e12, "peak_tflops": fma_peak,
                              "frac": alg["W_fwd"] * B / (fwd_ms * 1e-3) / 1e12 / fma_peak,
-                             "note": "dense-formulation flops (SURVEY 8d) / measured FFMA peak; the kernel is FMA-bound"}},
+                             "note": "dense-formulation flops (SURVEY 8d) / measured FFMA peak; the kernel is latency-bound on the LU pivot chain (DESIGN.md 3.4)"}},
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
