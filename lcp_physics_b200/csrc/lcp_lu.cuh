@@ -188,6 +188,27 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return r;
 }
 
+// Packed FP32 FMA (sm_100 FFMA2): d{0,1} = a{0,1} * b{0,1} + d{0,1} in ONE instruction. The pairs
+// must sit in even-aligned adjacent registers (ptxas then emits no moves). Used only in the
+// single-warp chain routines, which are bound by instruction issue (~1 instruction / 3 cycles).
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  unsigned long long d, a, b;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+// out{0,1} = a{0,1} * b{0,1} + c{0,1}
+__device__ __forceinline__ void ffma2_to(float& o0, float& o1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  unsigned long long d, a, b, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c0), "f"(c1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(d));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Diagonal block (ONE warp -- the critical path of the factorisation): P_b L U of the NB x NB block
 // with rows in REGISTERS and a ROLLED pivot loop. After eliminating a column every live row shifts
@@ -300,6 +321,107 @@ __device__ __forceinline__ void diag_rot_steps(int k_begin, int k_end, T (&a)[NB
   }
 }
 
+// fp32 variant with packed FMAs: two pivots per loop iteration so that every FFMA2 works on
+// even-aligned register pairs. Pivot k (OFF = 0) sits in a[0]: rows are updated in place (the dead
+// a[0] rides along in the first pair). Pivot k+1 (OFF = 1) sits in a[1]: the update writes two
+// registers lower, a[j-2] = a[j] - l u[j], which is the shift for both pivots at once. A row that was
+// pivot at an odd step therefore ends with its U row starting at a[1] (see the final store).
+template <int NB, int W, int OFF>
+__device__ __forceinline__ void diag_one_step2(int k, float (&a)[NB], float (&u)[NB], float& rinv, float& rm, float& myr,
+                                               bool& moved, float* D, int ld, float* stage, int* perm, float* Lt, int ldlt) {
+  constexpr int VC = 4, WV = W / VC, SL = NB + VC;
+  const int lane = threadIdx.x & 31;
+  const float tau = 1e-4f;
+  float* const st = stage + (k & 1) * SL;
+  {
+    const bool mine = lane == k;
+#pragma unroll
+    for (int c = 0; c < WV; ++c)
+      if (mine) *reinterpret_cast<float4*>(st + c * VC) = make_float4(a[c * VC], a[c * VC + 1], a[c * VC + 2], a[c * VC + 3]);
+    if (mine) st[NB] = rinv;
+    if (mine) st[NB + 1] = rm;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < WV; ++c) {
+    const float4 t = *reinterpret_cast<const float4*>(st + c * VC);
+    u[c * VC] = t.x; u[c * VC + 1] = t.y; u[c * VC + 2] = t.z; u[c * VC + 3] = t.w;
+  }
+  float piv = u[OFF];
+  float r = st[NB];
+  const float rs = st[NB + 1];
+  bool suspect = !(fabsf(piv) >= tau * rs && fabsf(piv) > 0.f);   // tier 1 (see diag_rot_steps)
+  if (suspect) {                                                   // tier 2: one REDUX over the column
+    float f = fabsf(a[OFF]);
+    if (f != f) f = INFINITY;
+    const unsigned cb = __reduce_max_sync(FULL, (lane >= k && lane < NB) ? __float_as_uint(f) : 0u);
+    suspect = !(fabsf(piv) >= 2.f * tau * __uint_as_float(cb) && fabsf(piv) > 0.f);
+  }
+  if (suspect) {                                                   // tier 3: arg-max search, interchange
+    float best = (lane >= k && lane < NB) ? fabsf(a[OFF]) : -1.f;
+    if (best != best) best = INFINITY;
+    int bi = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(FULL, best, o);
+      const int oi = __shfl_xor_sync(FULL, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (bi != k && !(fabsf(piv) >= tau * best && fabsf(piv) > 0.f)) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        const float fk = __shfl_sync(FULL, a[j], k), fb = __shfl_sync(FULL, a[j], bi);
+        if (lane == k) a[j] = fb; else if (lane == bi) a[j] = fk;
+        u[j] = fb;
+      }
+      {
+        const float fk = __shfl_sync(FULL, rm, k), fb = __shfl_sync(FULL, rm, bi);
+        if (lane == k) rm = fb; else if (lane == bi) rm = fk;
+      }
+      if (lane < k) {
+        const float t0 = D[(size_t)k * ld + lane], t1 = D[(size_t)bi * ld + lane];
+        D[(size_t)k * ld + lane] = t1;
+        D[(size_t)bi * ld + lane] = t0;
+        Lt[(size_t)lane * ldlt + k] = t1;
+        Lt[(size_t)lane * ldlt + bi] = t0;
+      }
+      if (lane == 0) { const int p0 = perm[k]; perm[k] = perm[bi]; perm[bi] = p0; }
+      moved = true;
+      __syncwarp();
+      piv = u[OFF];
+      r = fast_rcp(piv);
+    }
+  }
+  if (lane == k) myr = r;
+  const bool alive = lane > k && lane < NB;
+  const float l = a[OFF] * r;
+  if (alive) D[(size_t)lane * ld + k] = l;
+  if (alive) Lt[(size_t)k * ldlt + lane] = l;
+  const float nl = -l;
+  if (OFF == 0) {
+#pragma unroll
+    for (int i = 0; i < W / 2; ++i)
+      if (alive) ffma2(a[2 * i], a[2 * i + 1], nl, nl, u[2 * i], u[2 * i + 1]);
+    rinv = fast_rcp(a[1]);
+  } else {
+#pragma unroll
+    for (int i = 1; i < W / 2; ++i)
+      if (alive) ffma2_to(a[2 * i - 2], a[2 * i - 1], nl, nl, u[2 * i], u[2 * i + 1], a[2 * i], a[2 * i + 1]);
+    rinv = fast_rcp(a[0]);
+  }
+}
+
+template <int NB, int W>
+__device__ __forceinline__ void diag_rot_steps2(int k_begin, int k_end, float (&a)[NB], float (&u)[NB], float& rinv, float& rm,
+                                                float& myr, bool& moved, float* D, int ld, float* stage, int* perm, float* Lt,
+                                                int ldlt) {
+#pragma unroll 1
+  for (int k = k_begin; k < k_end; k += 2) {
+    diag_one_step2<NB, W, 0>(k, a, u, rinv, rm, myr, moved, D, ld, stage, perm, Lt, ldlt);
+    diag_one_step2<NB, W, 1>(k + 1, a, u, rinv, rm, myr, moved, D, ld, stage, perm, Lt, ldlt);
+  }
+}
+
 // Lt: transposed copy of the strictly-lower part (Lt[k][i] = L[i][k], leading dimension ldlt), so
 // that the look-ahead U12 piece reads columns of L as contiguous vectors.
 template <typename T, int MODE, int NB>
@@ -335,8 +457,14 @@ __device__ __noinline__ void diag_lu_rot(MPtr<T, MODE> Db, int ld, int o_perm_i,
       for (int c = 0; c < NV; ++c) {
         T t[VC];
         vec_get<T>(*reinterpret_cast<const V*>(ub + (size_t)p * ld + c * VC), t);
+        if constexpr (sizeof(T) == 4) {
+          const float nl = -l;
 #pragma unroll
-        for (int q = 0; q < VC; ++q) a[c * VC + q] = fma(-l, t[q], a[c * VC + q]);
+          for (int q = 0; q < VC; q += 2) ffma2(a[c * VC + q], a[c * VC + q + 1], nl, nl, t[q], t[q + 1]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < VC; ++q) a[c * VC + q] = fma(-l, t[q], a[c * VC + q]);
+        }
       }
     }
   }
@@ -351,16 +479,31 @@ __device__ __noinline__ void diag_lu_rot(MPtr<T, MODE> Db, int ld, int o_perm_i,
   for (int j = 0; j < NB; ++j) rm = fmax(rm, fabs(a[j]));
   T rinv = fast_rcp(a[0]);
   constexpr int Q4 = NB / 4;
-  diag_rot_steps<T, NB, NB>(0, Q4, a, u, rinv, rm, myr, moved, D, ld, stage, perm, Lt, ldlt);
-  diag_rot_steps<T, NB, 3 * Q4>(Q4, 2 * Q4, a, u, rinv, rm, myr, moved, D, ld, stage, perm, Lt, ldlt);
-  diag_rot_steps<T, NB, 2 * Q4>(2 * Q4, 3 * Q4, a, u, rinv, rm, myr, moved, D, ld, stage, perm, Lt, ldlt);
-  diag_rot_steps<T, NB, Q4>(3 * Q4, NB, a, u, rinv, rm, myr, moved, D, ld, stage, perm, Lt, ldlt);
-  // row i stopped shifting after step i: a[j] = U[i][i + j]
-  if (lane < NB) {
+  if constexpr (sizeof(T) == 4) {
+    diag_rot_steps2<NB, NB>(0, Q4, a, u, rinv, rm, myr, moved, D, ld, stage, perm, Lt, ldlt);
+    diag_rot_steps2<NB, 3 * Q4>(Q4, 2 * Q4, a, u, rinv, rm, myr, moved, D, ld, stage, perm, Lt, ldlt);
+    diag_rot_steps2<NB, 2 * Q4>(2 * Q4, 3 * Q4, a, u, rinv, rm, myr, moved, D, ld, stage, perm, Lt, ldlt);
+    diag_rot_steps2<NB, Q4>(3 * Q4, NB, a, u, rinv, rm, myr, moved, D, ld, stage, perm, Lt, ldlt);
+    // a row that was pivot at an even step: a[j] = U[i][i + j]; at an odd step: a[j] = U[i][i - 1 + j], j >= 1
+    if (lane < NB) {
+      const int off = lane & 1;
 #pragma unroll
-    for (int j = 0; j < NB; ++j)
-      if (lane + j < NB) D[(size_t)lane * ld + lane + j] = a[j];
-    (smem_base<T>() + o_rdiag)[lane] = myr;
+      for (int j = 0; j < NB; ++j)
+        if (j >= off && lane - off + j < NB) D[(size_t)lane * ld + lane - off + j] = a[j];
+      (smem_base<T>() + o_rdiag)[lane] = myr;
+    }
+  } else {
+    diag_rot_steps<T, NB, NB>(0, Q4, a, u, rinv, rm, myr, moved, D, ld, stage, perm, Lt, ldlt);
+    diag_rot_steps<T, NB, 3 * Q4>(Q4, 2 * Q4, a, u, rinv, rm, myr, moved, D, ld, stage, perm, Lt, ldlt);
+    diag_rot_steps<T, NB, 2 * Q4>(2 * Q4, 3 * Q4, a, u, rinv, rm, myr, moved, D, ld, stage, perm, Lt, ldlt);
+    diag_rot_steps<T, NB, Q4>(3 * Q4, NB, a, u, rinv, rm, myr, moved, D, ld, stage, perm, Lt, ldlt);
+    // row i stopped shifting after step i: a[j] = U[i][i + j]
+    if (lane < NB) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        if (lane + j < NB) D[(size_t)lane * ld + lane + j] = a[j];
+      (smem_base<T>() + o_rdiag)[lane] = myr;
+    }
   }
   if (lane == 0) *smem_int(o_flag_i) = moved ? 1 : 0;
 }
@@ -477,9 +620,17 @@ __device__ __forceinline__ void tri_piece(T (&a)[NB], const T* coef, int ldc, co
         if (c * VC + VC - 1 <= s_) continue;
         T t[VC];
         vec_get<T>(*reinterpret_cast<const V*>(cr + c * VC), t);
+        if constexpr (sizeof(T) == 4) {
+          // packed pairs; an entry <= s_ inside a pair is already dead, updating it is harmless
+          const float nx = -x;
 #pragma unroll
-        for (int q = 0; q < VC; ++q)
-          if (c * VC + q > s_) a[c * VC + q] = fma(-x, t[q], a[c * VC + q]);
+          for (int q = 0; q < VC; q += 2)
+            if (c * VC + q + 1 > s_) ffma2(a[c * VC + q], a[c * VC + q + 1], nx, nx, t[q], t[q + 1]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < VC; ++q)
+            if (c * VC + q > s_) a[c * VC + q] = fma(-x, t[q], a[c * VC + q]);
+        }
       }
     }
 #pragma unroll
@@ -620,6 +771,8 @@ __device__ __forceinline__ void lu_region(MPtr<T, MODE> Ab, int ld, int sz, int 
       named_bar_sync(2, 64);                                     // the two pieces see each other
       if (warp == 0) {
         named_bar_arrive(1, blockDim.x);                         // release them to everyone (warp 1 syncs below)
+        // (a separate two-warp rank_nb_update of block (k+1,k+1) was measured: its cold code costs more
+        // than the compact fused loop inside diag_lu_rot saves)
         const long long c1 = prof ? clock64() : 0;
         diag_lu_rot<T, MODE, NB>(Ab.plus((long long)r0 * ld + r0), ld, o_perm_i + r0, o_rdiag + r0,
                                  lv.o_flag_i + ((kb + 1) & 1), lv.o_stage, lv.o_lt, lv.ldlt, 1);
@@ -787,6 +940,18 @@ __device__ __noinline__ void split_schur(TView<T, MODE> v, const T* __restrict__
       }
     }
   }
+  // T22 = R22 + diag comes from the L2 copy: issue those loads now, they complete under the spill
+  T t22v[TR][2 * VC];
+#pragma unroll
+  for (int r = 0; r < TR; ++r)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+      for (int q = 0; q < VC; ++q) {
+        const int i = rbase + 4 * r, c = (hh ? c1 : c0) + q;
+        const int gi = m1 + i, gj = m1 + c;             // global indices in the padded matrix
+        t22v[r][hh * VC + q] = (have && i < n2 && c < n2 && gi < m_real && gj < m_real) ? R22[(size_t)i * ldr + c] : T(0);
+      }
   __syncthreads();                       // all reads of U12 done
   // spill U12 (final) to L2: main rows [0,m1) x cols [m1,mp) -> u12 [m1, n2]
   for (int t = threadIdx.x; t < m1 * (n2 / VC); t += blockDim.x) {
@@ -807,8 +972,8 @@ __device__ __noinline__ void split_schur(TView<T, MODE> v, const T* __restrict__
         T out[VC];
 #pragma unroll
         for (int q = 0; q < VC; ++q) {
-          const int gi = m1 + i, gj = m1 + c + q;       // global indices in the padded matrix
-          T t22 = (gi < m_real && gj < m_real) ? R22[(size_t)i * ldr + c + q] : T(0);
+          const int gi = m1 + i, gj = m1 + c + q;
+          T t22 = t22v[r][hh * VC + q];
           if (gi == gj) t22 += dinv[gi];
           out[q] = t22 - acc[r][hh * VC + q];
         }

@@ -264,6 +264,13 @@ __device__ __noinline__ bool prefactor(SceneCtx<T, MODE>& c, int* flag) {
   const int n = c.n, m = c.m, e = c.e, tid = threadIdx.x, NT = blockDim.x;
   Vecs<T> v = c.vecs();
   if (tid == 0) *flag = 0;
+  if (!c.Rsaved) {
+    // F is read once, at the very end of this phase (R = G Q^-1 G^T + F), straight from HBM: pull it
+    // towards L2 now so that the epilogue does not wait on DRAM
+    const char* fp = reinterpret_cast<const char*>(c.F);
+    const size_t lines = ((size_t)m * m * sizeof(T) + 127) / 128;
+    for (size_t l = tid; l < lines; l += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + l * 128));
+  }
   // Q^{-1} (:362 factors Q; we keep the inverse so later Q-solves are GEMVs). Diagonal Q -- every
   // mass matrix the engine builds (world.py:57-61) -- is inverted directly.
   int offdiag = 0;
