@@ -618,6 +618,7 @@ __device__ __forceinline__ void tri_piece(T (&a)[NB], const T* coef, int ldc, co
 #pragma unroll
       for (int c = 0; c < NV; ++c) {
         if (c * VC + VC - 1 <= s_) continue;
+        if (c >= NV - g) continue;                 // past the block: only dead registers would be touched
         T t[VC];
         vec_get<T>(*reinterpret_cast<const V*>(cr + c * VC), t);
         if constexpr (sizeof(T) == 4) {
@@ -647,6 +648,7 @@ __device__ __noinline__ void lookahead_u12(MPtr<T, MODE> Db, int ld, int o_lt, i
   T a[NB];
 #pragma unroll
   for (int i = 0; i < NB; ++i) a[i] = B[(size_t)i * ld + lj];
+  __syncwarp();                                    // lanes >= NB mirror the last column: reads before its stores
   tri_piece<T, NB, false>(a, Lt, ldlt, nullptr, [&](int p, T x) { if (lane < NB) B[(size_t)p * ld + lj] = x; });
   __syncwarp();
 }
