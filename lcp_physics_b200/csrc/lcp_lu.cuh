@@ -513,6 +513,8 @@ __device__ __noinline__ void diag_lu_rot(MPtr<T, MODE> Db, int ld, int o_perm_i,
 // register array per thread):
 //   panel_cols: U12 columns [c_lo, c_hi) of rows k0..k0+NB of `Ub`:  U12 = L11^{-1} A12  (one column
 //       per thread, left-looking: rows of L11 are read as broadcast vectors)
+//   (a rolled tri_piece variant of panel_rows was measured: 14 % slower than this unrolled form, whose
+//   instruction count is lower although a quarter of its samples wait on instruction fetch)
 //   panel_rows: L21 rows [r_lo, r_hi) of `Cb`:  L21 = A21 U11^{-1}  (one row per thread, right-looking:
 //       rows of U11 are read as broadcast vectors, rdiag = 1/diag(U11))
 // tix in [0, nthr): index of this thread among the participating ones (tix < 0: not taking part).
