@@ -27,7 +27,7 @@ struct Plan {
   int off_T, off_L, off_G, off_Qi, off_vec;   // shared offsets, in elements
   int smem_bytes;
   long long ws_per_cta;       // workspace elements per CTA
-  long long w_Qi, w_R, w_T, w_U12, w_X, w_XA, w_S11, w_V, w_W;
+  long long w_Qi, w_R, w_T, w_U12, w_X, w_XA, w_S11, w_V, w_W, w_Fell, w_Gell;
 };
 
 // phases for the optional cycle counters
@@ -83,6 +83,12 @@ struct SceneCtx {
   bool Rsaved;                // R points at a matrix saved by the forward pass (read-only)
   bool qdiag;                 // Q is diagonal: Q^{-1} v is an element-wise product with Vecs::qinv
   bool t_prefetched;          // R is already on its way into T's shared region (prefetch_T)
+  bool f_ell;                 // F has <= 4 non-zeros in every row: F z uses the ELL copy (Fell_v / Fell_i)
+  T* Fell_v; int* Fell_i;     // [4][m] values / column indices (L2 workspace)
+  bool g_ell_built;           // build_g_ell already ran for this scene (inside prefactor, from the staged copy)
+  bool g_ell;                 // G (L2-resident) has <= 8 non-zeros per row and <= 32 per column: GEMVs use ELL copies
+  T* Gr_v; int* Gr_i;         // [8][m]  row form:    G x
+  T* Gc_v; int* Gc_i;         // [32][n] column form: G^T w
   int stage_ld;               // > 0: G may be staged in T's shared region with this leading dimension
   const T* Gsrc;              // this scene's G in global memory
   int* lu_flag;
@@ -258,6 +264,132 @@ __device__ __forceinline__ void gram_diag(const T* __restrict__ Gs, int ldg, con
   __syncthreads();
 }
 
+// ------------------------------------------------------------------ sparse copy of F
+// Every F the engine builds (engines.py:66-72: E, mu, -E^T blocks) has at most 3 non-zeros per row,
+// but the API hands it over dense (m^2 = 256 KB at cfg 3) and the residual needs F z every iteration.
+// One pass per scene compacts the rows into ELL form (4 slots per row, in the L2 workspace); if any
+// row has more non-zeros the dense GEMV stays. Sums run over the same non-zero terms as the dense
+// product (adding zeros is exact), only their order differs.
+template <typename T, int MODE>
+__device__ __noinline__ void build_f_ell(SceneCtx<T, MODE>& c) {
+  constexpr int KF = 4, CH = 8;                     // CH x 32 columns of a row in flight per lane
+  const int m = c.m, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int dense = 0;
+  for (int r = warp; r < m; r += nw) {
+    const T* row = c.F + (size_t)r * m;
+    int cnt = 0;
+    for (int j0 = 0; j0 < m; j0 += 32 * CH) {
+      T v[CH];
+#pragma unroll
+      for (int q = 0; q < CH; ++q) { const int j = j0 + q * 32 + lane; v[q] = j < m ? row[j] : T(0); }
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        const bool nz = v[q] != T(0);
+        const unsigned mask = __ballot_sync(FULL, nz);
+        const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+        if (nz && pos < KF) { c.Fell_v[(size_t)pos * m + r] = v[q]; c.Fell_i[(size_t)pos * m + r] = j0 + q * 32 + lane; }
+        cnt += __popc(mask);
+      }
+    }
+    if (cnt > KF) dense = 1;
+    if (lane >= cnt && lane < KF) { c.Fell_v[(size_t)lane * m + r] = T(0); c.Fell_i[(size_t)lane * m + r] = 0; }
+  }
+  dense = __syncthreads_or(dense);
+  c.f_ell = !dense;
+}
+
+// ------------------------------------------------------------------ sparse copies of G
+// Contact Jacobians touch two bodies: <= 6 non-zeros per row of G (world.py:166-212), and a body
+// column collects its contacts' rows. When G does not fit in shared memory every G x / G^T w of the
+// iteration (5 per iteration) streams the dense 96 KB from L2; the ELL copies (8 slots per row,
+// 32 per column, built once per scene by ordered ballot scans -- deterministic) cut that to 16 KB.
+// Rows / columns with more non-zeros keep the dense path.
+template <typename T, int MODE>
+__device__ __noinline__ void build_g_ell(SceneCtx<T, MODE>& c, const T* Gp, int ldg) {
+  // Gp/ldg: where to scan G from -- the copy staged in shared memory by prefactor when there is one
+  // (the column scan is strided), else the global matrix
+  constexpr int KR = 8, KC = 32, CH = 4;
+  const int m = c.m, n = c.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  c.g_ell_built = true;
+  if (c.G != c.Gsrc) { c.g_ell = false; return; }          // G lives in shared memory: dense is fine
+  int dense = 0;
+  for (int r = warp; r < m; r += nw) {                     // rows
+    const T* row = Gp + (size_t)r * ldg;
+    int cnt = 0;
+    for (int j0 = 0; j0 < n; j0 += 32 * CH) {
+      T v[CH];
+#pragma unroll
+      for (int q = 0; q < CH; ++q) { const int j = j0 + q * 32 + lane; v[q] = j < n ? row[j] : T(0); }
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        const bool nz = v[q] != T(0);
+        const unsigned mask = __ballot_sync(FULL, nz);
+        const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+        if (nz && pos < KR) { c.Gr_v[(size_t)pos * m + r] = v[q]; c.Gr_i[(size_t)pos * m + r] = j0 + q * 32 + lane; }
+        cnt += __popc(mask);
+      }
+    }
+    if (cnt > KR) dense = 1;
+    if (lane >= cnt && lane < KR) { c.Gr_v[(size_t)lane * m + r] = T(0); c.Gr_i[(size_t)lane * m + r] = 0; }
+  }
+  for (int j = warp; j < n; j += nw) {                     // columns
+    const T* col = Gp + j;
+    int cnt = 0;
+    for (int i0 = 0; i0 < m; i0 += 32 * CH) {
+      T v[CH];
+#pragma unroll
+      for (int q = 0; q < CH; ++q) { const int i = i0 + q * 32 + lane; v[q] = i < m ? col[(size_t)i * ldg] : T(0); }
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        const bool nz = v[q] != T(0);
+        const unsigned mask = __ballot_sync(FULL, nz);
+        const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+        if (nz && pos < KC) { c.Gc_v[(size_t)pos * n + j] = v[q]; c.Gc_i[(size_t)pos * n + j] = i0 + q * 32 + lane; }
+        cnt += __popc(mask);
+      }
+    }
+    if (cnt > KC) dense = 1;
+    if (lane >= cnt) { c.Gc_v[(size_t)lane * n + j] = T(0); c.Gc_i[(size_t)lane * n + j] = 0; }
+  }
+  dense = __syncthreads_or(dense);
+  c.g_ell = !dense;
+}
+
+// G x and G^T w through whichever form is active (same epilogue interface as the dense GEMVs)
+template <typename T, int MODE, typename Epi>
+__device__ __forceinline__ void gemv_G_rows(SceneCtx<T, MODE>& c, const T* x, Epi epi, const Team& tm) {
+  if (c.g_ell) {
+    const int m = c.m;
+    for (int i = tm.tid; i < m; i += tm.nt) {
+      T acc = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc = fma(c.Gr_v[(size_t)k * m + i], x[c.Gr_i[(size_t)k * m + i]], acc);
+      epi(i, acc);
+    }
+    tm.sync();
+  } else {
+    gemv_rows_v(c.G, c.ldG, c.m, c.n, x, epi, tm);
+  }
+}
+template <typename T, int MODE, typename Epi>
+__device__ __forceinline__ void gemv_G_cols(SceneCtx<T, MODE>& c, const T* w, T* scratch, Epi epi, const Team& tm) {
+  if (c.g_ell) {
+    const int n = c.n;
+    for (int j = tm.tid; j < n; j += tm.nt) {
+      T acc0 = 0, acc1 = 0;
+#pragma unroll
+      for (int k = 0; k < 32; k += 2) {
+        acc0 = fma(c.Gc_v[(size_t)k * n + j], w[c.Gc_i[(size_t)k * n + j]], acc0);
+        acc1 = fma(c.Gc_v[(size_t)(k + 1) * n + j], w[c.Gc_i[(size_t)(k + 1) * n + j]], acc1);
+      }
+      epi(j, acc0 + acc1);
+    }
+    tm.sync();
+  } else {
+    gemv_cols_v(c.G, c.ldG, c.m, c.n, w, scratch, epi, tm);
+  }
+}
+
 // ------------------------------------------------------------------ pre_factor_kkt (pdipm.py:357-408)
 template <typename T, int MODE>
 __device__ __noinline__ bool prefactor(SceneCtx<T, MODE>& c, int* flag) {
@@ -318,6 +450,7 @@ __device__ __noinline__ bool prefactor(SceneCtx<T, MODE>& c, int* flag) {
       }
       __syncthreads();
       gram_diag<T>(Gs, ldgs, qd, c.F, c.R, m, n);
+      build_g_ell(c, Gs, ldgs);                                  // while the staged copy is still there
     } else {
       __syncthreads();
       gram_diag<T>(c.G, c.ldG, qd, c.F, c.R, m, n);
@@ -542,7 +675,7 @@ __device__ __noinline__ void solve_kkt(SceneCtx<T, MODE>& c, int o_rx, int o_rs,
     } else {
       gemv_rows_v(c.Qi, c.ldQi, n, n, rx, [&](int i, T a) { t[i] = a; });
     }
-    gemv_rows_v(c.G, c.ldG, m, n, t, [&](int i, T a) { v.hz[i] = a + rs[i] / d[i] - (rz ? rz[i] : T(0)); });   // :337-340
+    gemv_G_rows(c, t, [&](int i, T a) { v.hz[i] = a + rs[i] / d[i] - (rz ? rz[i] : T(0)); }, Team::cta());   // :337-340
     if (e > 0) gemv_rows_v(c.A, n, e, n, t, [&](int i, T a) { v.hy[i] = a - (ry ? ry[i] : T(0)); });
   } else {
     for (int i = tid; i < m; i += NT) v.hz[i] = rs[i] / d[i] - (rz ? rz[i] : T(0));
@@ -562,7 +695,7 @@ __device__ __noinline__ void solve_kkt(SceneCtx<T, MODE>& c, int o_rx, int o_rs,
   }
   __syncthreads();
   T* g1 = v.tn2;                                                 // :344-349
-  gemv_cols_v(c.G, c.ldG, m, n, dz, v.scratch, [&](int j, T a) { g1[j] = -(rx ? rx[j] : T(0)) - a; });
+  gemv_G_cols(c, dz, v.scratch, [&](int j, T a) { g1[j] = -(rx ? rx[j] : T(0)) - a; }, Team::cta());
   if (e > 0) gemv_cols_v(c.A, n, e, n, dy, v.scratch, [&](int j, T a) { g1[j] -= a; });
   if (c.qdiag) {
     for (int i = tid; i < n; i += NT) dx[i] = v.qinv[i] * g1[i];
@@ -620,6 +753,10 @@ __device__ void setup_ctx(SceneCtx<T, MODE>& c, const Plan& P, T* sm, T* ws, int
   c.tv.u12 = ws + P.w_U12;
   c.R = ws + P.w_R; c.X = ws + P.w_X; c.XA = ws + P.w_XA; c.S11 = ws + P.w_S11;
   c.Vm = ws + P.w_V; c.W = ws + P.w_W;
+  c.Fell_v = ws + P.w_Fell; c.Fell_i = reinterpret_cast<int*>(ws + P.w_Fell + (long long)4 * P.m); c.f_ell = false;
+  c.Gr_v = ws + P.w_Gell; c.Gr_i = reinterpret_cast<int*>(ws + P.w_Gell + (long long)8 * P.m);
+  c.Gc_v = ws + P.w_Gell + (long long)16 * P.m; c.Gc_i = reinterpret_cast<int*>(ws + P.w_Gell + (long long)16 * P.m + (long long)32 * P.n);
+  c.g_ell = false; c.g_ell_built = false;
   c.Rsaved = false; c.qdiag = false; c.t_prefetched = false; c.stage_ld = P.stage_ld; c.Gsrc = nullptr;
   c.lu_flag = lu_flag;
   c.prof = prof ? prof + (size_t)blockIdx.x * PH_COUNT : nullptr;
@@ -635,7 +772,7 @@ __device__ void setup_ctx(SceneCtx<T, MODE>& c, const Plan& P, T* sm, T* ws, int
 template <typename T, int MODE>
 __device__ void bind_scene(SceneCtx<T, MODE>& c, const Plan& P, T* sm, const T* Q, const T* G, const T* A, const T* F) {
   const int n = P.n, m = P.m;
-  c.Q = Q; c.A = A; c.F = F; c.Gsrc = G;
+  c.Q = Q; c.A = A; c.F = F; c.Gsrc = G; c.g_ell_built = false; c.g_ell = false; c.f_ell = false;
   {   // padded tails: a NaN produced by the previous scene must not leak into this one
     Vecs<T> v = c.vecs();
     for (int i = P.m + threadIdx.x; i < P.mp; i += blockDim.x) {
@@ -689,6 +826,8 @@ __global__ void __launch_bounds__(512, 1) lcp_forward_kernel(const FwdArgs<T> a)
       __syncthreads();
       continue;
     }
+    build_f_ell(c);
+    if (!c.g_ell_built) build_g_ell(c, c.Gsrc, n);
     prof_lap(c, PH_PREFACTOR);
 
     // ---- initial point: d = 1, rhs (p, 0, -h, -b)                 :58-63
@@ -729,7 +868,7 @@ __global__ void __launch_bounds__(512, 1) lcp_forward_kernel(const FwdArgs<T> a)
       }
       if (in_team) {
         const int TN = tm.nt;
-        gemv_cols_v(c.G, c.ldG, m, n, v.z, v.scratch, [&](int j, T acc) { v.rx[j] = acc; }, tm);
+        gemv_G_cols(c, v.z, v.scratch, [&](int j, T acc) { v.rx[j] = acc; }, tm);
         if (e > 0) gemv_cols_v(c.A, n, e, n, v.y, v.scratch, [&](int j, T acc) { v.rx[j] = acc + v.rx[j]; }, tm);
         if (c.qdiag) {
           for (int i = tid; i < n; i += TN) v.rx[i] = v.rx[i] + c.Q[(size_t)i * n + i] * v.x[i] + p[i];
@@ -737,8 +876,18 @@ __global__ void __launch_bounds__(512, 1) lcp_forward_kernel(const FwdArgs<T> a)
         } else {
           gemv_rows_v(c.Q, n, n, n, v.x, [&](int i, T acc) { v.rx[i] = v.rx[i] + acc + p[i]; }, tm);
         }
-        gemv_rows_v(c.G, c.ldG, m, n, v.x, [&](int i, T acc) { v.rz[i] = acc + v.s[i] - h[i]; }, tm);
-        gemv_rows_v(c.F, m, m, m, v.z, [&](int i, T acc) { v.rz[i] -= acc; }, tm);
+        gemv_G_rows(c, v.x, [&](int i, T acc) { v.rz[i] = acc + v.s[i] - h[i]; }, tm);
+        if (c.f_ell) {
+          for (int i = tid; i < m; i += TN) {
+            T acc = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc = fma(c.Fell_v[(size_t)k * m + i], v.z[c.Fell_i[(size_t)k * m + i]], acc);
+            v.rz[i] -= acc;
+          }
+          tm.sync();
+        } else {
+          gemv_rows_v(c.F, m, m, m, v.z, [&](int i, T acc) { v.rz[i] -= acc; }, tm);
+        }
         if (e > 0) gemv_rows_v(c.A, n, e, n, v.x, [&](int i, T acc) { v.ry[i] = acc - b[i]; }, tm);
         T q[4] = {0, 0, 0, 0};                                      // s.z, |rz|^2, |ry|^2, |rx|^2
         for (int i = tid; i < m; i += TN) { q[0] += v.s[i] * v.z[i]; q[1] += v.rz[i] * v.rz[i]; }

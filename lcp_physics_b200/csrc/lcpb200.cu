@@ -122,6 +122,8 @@ static int make_plan(lcpb200_handle_s* h) {
   P.w_S11 = ws; ws += al4((long long)e * e);
   P.w_V = ws; ws += al4((long long)m * e);
   P.w_W = ws; ws += al4((long long)e * m);
+  P.w_Fell = ws; ws += al4((long long)m * 8);          // F in ELL form: 4 values + 4 column indices per row
+  P.w_Gell = ws; ws += al4((long long)16 * m + (long long)64 * n);   // G in row-ELL (8/row) and column-ELL (32/column) form
   P.ws_per_cta = ws;
   return 0;
 }

@@ -124,6 +124,42 @@ def test_forward_vs_oracle_seeded_fp32(cfg):
     assert float(mine.max()) <= max(1e-2, 2 * float(own.max())), (mine, own)
 
 
+# Block-structure variants of the look-ahead LU: 2, 3, 6 and 10 diagonal blocks, all-in-shared-memory
+# (mode 0), split (mode 1) and the L2-resident plan (mode 2, m = 384 in fp64), with and without
+# equality rows; every plan must reproduce the oracle.
+VARIANTS = {
+    # name: (nb, nc, fd, e, dtype, B)
+    "m64_fp32_2blocks": (8, 16, 2, 0, torch.float32, 12),
+    "m96_fp32_3blocks_e2": (12, 24, 2, 2, torch.float32, 12),
+    "m96_fp64_6blocks_e2": (12, 24, 2, 2, torch.float64, 12),
+    "m160_fp64_split": (20, 40, 2, 0, torch.float64, 8),
+    "m384_fp64_l2_plan": (24, 96, 2, 0, torch.float64, 3),
+}
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_plan_variants_match_oracle(name):
+    from lcp_physics_b200 import solve_forward, _lib
+    from lcp_physics_b200.scenes import make_scenes
+    from oracle import pdipm_oracle as po
+    nb, nc, fd, e, dtype, B = VARIANTS[name]
+    inp64 = make_scenes(B, nb, nc, fd=fd, e=e, dtype=torch.float64, seed=77)
+    ref = po.lcp_forward(*inp64, max_iter=10).zhat
+    inp = tuple(t.to(dtype) for t in inp64)
+    zhat = solve_forward(*_cuda(inp), max_iter=10)[0].cpu().double()
+    err = rel_err(zhat, ref)
+    if dtype == torch.float64:
+        assert err.max() < 1e-6, (name, err)
+    else:
+        assert (err < 1e-3).float().mean() >= 0.8 and err.max() < 2e-2, (name, err)
+    n, m = 3 * nb, nc * (2 + fd)
+    desc = _lib.get_handle(dtype, n, m, e, 0).describe()
+    if name == "m384_fp64_l2_plan":
+        assert "T:L2" in desc, desc
+    if name == "m160_fp64_split":
+        assert "split" in desc, desc
+
+
 def test_autograd_through_lcpfunction_matches_oracle():
     from lcp_physics_b200 import LCPFunction
     from lcp_physics_b200.scenes import make_scenes
