@@ -160,6 +160,20 @@ def test_plan_variants_match_oracle(name):
         assert "split" in desc, desc
 
 
+@pytest.mark.parametrize("n,m,e", [(96, 256, 0), (48, 160, 4)])
+def test_dense_inputs_at_split_plan_sizes_fp64(n, m, e):
+    """Fully dense Q, G, F (no contact structure) at sizes where G and Q^-1 live in L2 and T is split:
+    the dense Q inverse, the dense Gram GEMMs and the dense-GEMV fallbacks of the ELL paths."""
+    from lcp_physics_b200 import solve_forward
+    from lcp_physics_b200.scenes import make_dense_random
+    from oracle import pdipm_oracle as po
+    inp = make_dense_random(3, n, m, e=e, dtype=torch.float64, seed=11)
+    ref = po.lcp_forward(*inp, max_iter=10)
+    out = solve_forward(*_cuda(inp), max_iter=10)
+    assert rel_err(out[0].cpu(), ref.zhat).max() < 1e-6
+    assert bool(torch.isfinite(out[0]).all())
+
+
 def test_autograd_through_lcpfunction_matches_oracle():
     from lcp_physics_b200 import LCPFunction
     from lcp_physics_b200.scenes import make_scenes
