@@ -610,6 +610,13 @@ __device__ __forceinline__ void tri_piece(T (&a)[NB], const T* coef, int ldc, co
   constexpr int VC = VecOf<T>::VC, NV = NB / VC;
 #pragma unroll 1
   for (int g = 0; g < NV; ++g) {
+    // vector c of a coefficient row covers positions (g + c) VC ..; past the block (c >= NV - g) only
+    // dead registers would be updated, so those loads are clamped onto the last in-block vector --
+    // no read ever leaves the block (the neighbouring block is being written by the other piece),
+    // and no branch enters the unrolled body
+    int coff[NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) coff[c] = min(c, NV - 1 - g) * VC;
 #pragma unroll
     for (int s_ = 0; s_ < VC; ++s_) {
       const int p = g * VC + s_;
@@ -620,9 +627,8 @@ __device__ __forceinline__ void tri_piece(T (&a)[NB], const T* coef, int ldc, co
 #pragma unroll
       for (int c = 0; c < NV; ++c) {
         if (c * VC + VC - 1 <= s_) continue;
-        if (c >= NV - g) continue;                 // past the block: only dead registers would be touched
         T t[VC];
-        vec_get<T>(*reinterpret_cast<const V*>(cr + c * VC), t);
+        vec_get<T>(*reinterpret_cast<const V*>(cr + coff[c]), t);
         if constexpr (sizeof(T) == 4) {
           // packed pairs; an entry <= s_ inside a pair is already dead, updating it is harmless
           const float nx = -x;
