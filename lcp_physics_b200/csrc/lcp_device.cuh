@@ -189,276 +189,4 @@ __device__ __forceinline__ void invert_inplace(T* A, int lda, int n, int* flag, 
   }
 }
 
-// ---------------------------------------------------------------- blocked pivot-free LU with inverted diagonal blocks
-// One warp: factor the NB x NB block at D (ld) as P_b L U and overwrite it with
-// [strict-lower(inv L) \ upper(inv U)] (unit diagonal of L implicit). Lane i holds physical row i
-// during elimination; perm[i] = physical row chosen as i-th pivot. Returns (warp-uniform) whether
-// the permutation is not the identity.
-//
-// Pivoting: the natural row is kept unless its pivot is below tau * (largest entry the row had when
-// the block was loaded) -- a shuffle-free scale, so the common path costs two broadcasts per pivot;
-// only then a full |max| search over the unused rows of the block runs (getf2 restricted to the
-// block). Measured (DESIGN.md "Pivoting"): eager swaps inside a block HURT fp32 trajectory parity,
-// never swapping leaves exact-zero pivots (0/0 -> NaN) on converged scenes.
-// This routine is a single-warp dependent chain (the critical path of the whole factorisation):
-// the two triangular inverses are interleaved in one loop so their chains overlap.
-template <typename T, int NB>
-__device__ __forceinline__ bool diag_block_factor_invert(T* D, int ld, int kb, int* perm) {
-  (void)kb;
-  const int lane = threadIdx.x & 31;
-  const int li = lane < NB ? lane : NB - 1;      // lanes >= NB mirror the last row and never store
-  T a[NB], x[NB];
-  T rmax = 0;
-#pragma unroll
-  for (int j = 0; j < NB; ++j) { a[j] = D[(size_t)li * ld + j]; rmax = fmax(rmax, fabs(a[j])); }
-  const T tau = (sizeof(T) == 4) ? T(1e-4) : T(1e-8);
-  unsigned alive = (NB == 32) ? FULL : ((1u << NB) - 1u);
-  bool done = lane >= NB;
-  int myord = lane;
-  bool moved = false;
-#pragma unroll
-  for (int k = 0; k < NB; ++k) {
-    const int nat = __ffs(alive) - 1;            // natural pivot row (uniform)
-    int pl = nat;
-    T ukk = __shfl_sync(FULL, a[k], nat);
-    const T rs = __shfl_sync(FULL, rmax, nat);
-    if (!(fabs(ukk) >= tau * rs && fabs(ukk) > T(0))) {     // rare: search the unused rows
-      T best = done ? T(-1) : fabs(a[k]);
-      if (best != best) best = INFINITY;         // NaN: take it, everything is NaN anyway
-      int bi = lane;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const T ov = __shfl_xor_sync(FULL, best, o);
-        const int oi = __shfl_xor_sync(FULL, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-      }
-      pl = bi;
-      ukk = __shfl_sync(FULL, a[k], pl);
-    }
-    alive &= ~(1u << pl);
-    if (lane == k) myord = pl;
-    moved |= (pl != k);
-    if (lane == pl) done = true;
-    const T r = T(1) / ukk;
-    const bool upd = !done;
-    const T l = a[k] * r;
-    if (upd) a[k] = l;
-#pragma unroll
-    for (int j = k + 1; j < NB; ++j) {
-      const T ukj = __shfl_sync(FULL, a[j], pl);
-      if (upd) a[j] = fma(-l, ukj, a[j]);
-    }
-  }
-  if (moved) {                                   // lane i <- row of its pivot lane
-#pragma unroll
-    for (int j = 0; j < NB; ++j) a[j] = __shfl_sync(FULL, a[j], myord);
-  }
-  if (lane < NB) perm[lane] = myord;
-  // reciprocal of the own diagonal entry of U, off the dependent chain
-  T dg = T(1);
-#pragma unroll
-  for (int j = 0; j < NB; ++j)
-    if (j == lane) dg = a[j];
-  const T rown = T(1) / dg;
-#pragma unroll
-  for (int j = 0; j < NB; ++j) x[j] = (j == lane) ? T(1) : T(0);
-  // inv(L) by row-oriented forward substitution (ascending k) and inv(U) by row-oriented back
-  // substitution (descending kk), interleaved; they touch disjoint halves of x in every lane.
-#pragma unroll
-  for (int k = 0; k < NB; ++k) {
-    {
-      const bool below = lane > k;
-      const T lik = a[k];
-#pragma unroll
-      for (int j = 0; j < k; ++j) {
-        const T xkj = __shfl_sync(FULL, x[j], k);
-        if (below) x[j] = fma(-lik, xkj, x[j]);
-      }
-      if (below) x[k] -= lik;
-    }
-    {
-      const int kk = NB - 1 - k;
-      const T rk = __shfl_sync(FULL, rown, kk);
-      const bool above = lane < kk;
-      const T uik = a[kk];
-#pragma unroll
-      for (int j = kk; j < NB; ++j) {
-        if (lane == kk) x[j] *= rk;
-        const T xkj = __shfl_sync(FULL, x[j], kk);
-        if (above) x[j] = fma(-uik, xkj, x[j]);
-      }
-    }
-  }
-  // the unit diagonal of inv(L) is implicit: x[lane] currently holds inv(U)[lane][lane]
-  if (lane < NB) {
-#pragma unroll
-    for (int j = 0; j < NB; ++j) D[(size_t)lane * ld + j] = x[j];
-  }
-  return moved;
-}
-
-// A[m,m] (lda) <- blocked LU (pdipm.py:431), P A = L U with P block-diagonal: partial pivoting
-// is restricted to the NB rows of the current diagonal block (the reference pivots over the
-// whole column on CPU tensors and not at all on CUDA tensors, pdipm.py:18; block-local pivoting
-// removes the exact-zero pivots of the pivot-free variant at one warp's cost). perm[i] = source
-// row of row i (shared, m ints; `flag` one shared int). Diagonal NB x NB blocks are left
-// INVERTED so that the later vector solves are block GEMVs instead of dependent chains.
-template <typename T>
-__device__ __forceinline__ void lu_blocked(T* A, int lda, int m, int* perm, int* flag) {
-  constexpr int NB = Blk<T>::NB;
-  const int tid = threadIdx.x, NT = blockDim.x;
-  for (int k0 = 0; k0 < m; k0 += NB) {
-    const int kb = min(NB, m - k0);
-    T* D = A + (size_t)k0 * lda + k0;
-    if (tid < 32) {
-      const bool moved = diag_block_factor_invert<T, NB>(D, lda, kb, perm + k0);
-      if (tid == 0) *flag = moved ? 1 : 0;
-    }
-    __syncthreads();
-    if (*flag) {
-      // apply the block's row interchanges to the columns left and right of the diagonal block;
-      // each thread owns one column, so no barrier is needed between its reads and writes
-      for (int c = tid; c < m - kb; c += NT) {
-        const int col = c < k0 ? c : c + kb;
-        T tmp[NB];
-#pragma unroll
-        for (int r = 0; r < NB; ++r)
-          if (r < kb) tmp[r] = A[(size_t)(k0 + perm[k0 + r]) * lda + col];
-#pragma unroll
-        for (int r = 0; r < NB; ++r)
-          if (r < kb) A[(size_t)(k0 + r) * lda + col] = tmp[r];
-      }
-      __syncthreads();
-    }
-    const int r0 = k0 + kb, rem = m - r0;
-    if (rem <= 0) break;
-    // panels: U12 = inv(L11) A12 (one column per task), L21 = A21 inv(U11) (one row per task)
-    for (int t = tid; t < 2 * rem; t += NT) {
-      T a[NB], y[NB];
-      if (t < rem) {
-        T* col = A + (size_t)k0 * lda + r0 + t;
-#pragma unroll
-        for (int r = 0; r < NB; ++r) a[r] = (r < kb) ? col[(size_t)r * lda] : T(0);
-#pragma unroll
-        for (int r = 0; r < NB; ++r) {
-          T acc = a[r];
-#pragma unroll
-          for (int q = 0; q < r; ++q)
-            if (r < kb) acc += D[(size_t)r * lda + q] * a[q];
-          y[r] = acc;
-        }
-#pragma unroll
-        for (int r = 0; r < NB; ++r)
-          if (r < kb) col[(size_t)r * lda] = y[r];
-      } else {
-        T* row = A + (size_t)(r0 + t - rem) * lda + k0;
-#pragma unroll
-        for (int c = 0; c < NB; ++c) a[c] = (c < kb) ? row[c] : T(0);
-#pragma unroll
-        for (int c = 0; c < NB; ++c) {
-          T acc = 0;
-#pragma unroll
-          for (int r = 0; r <= c; ++r)
-            if (c < kb) acc += a[r] * D[(size_t)r * lda + c];
-          y[c] = acc;
-        }
-#pragma unroll
-        for (int c = 0; c < NB; ++c)
-          if (c < kb) row[c] = y[c];
-      }
-    }
-    __syncthreads();
-    // trailing update A22 -= L21 U12, 4x4 register tiles
-    const int tt = (rem + 3) >> 2;
-    for (int t = tid; t < tt * tt; t += NT) {
-      const int ti = t / tt, tj = t - ti * tt;
-      const int i0 = r0 + 4 * ti, j0 = r0 + 4 * tj;
-      int ir[4], jc[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) { ir[r] = min(i0 + r, m - 1); jc[r] = min(j0 + r, m - 1); }
-      T acc[4][4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0;
-      for (int k = 0; k < kb; ++k) {
-        T l[4], u[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) l[r] = A[(size_t)ir[r] * lda + k0 + k];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) u[c] = A[(size_t)(k0 + k) * lda + jc[c]];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) acc[r][c] += l[r] * u[c];
-      }
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (i0 + r < m && j0 + c < m) A[(size_t)(i0 + r) * lda + j0 + c] -= acc[r][c];
-    }
-    __syncthreads();
-  }
-}
-
-// v[m] (shared) <- (LU)^{-1} v using the factors left by lu_blocked. Right-looking block
-// substitution: diagonal step = multiply by the stored block inverse (one warp), update step
-// = one thread per remaining row.
-template <typename T>
-__device__ __forceinline__ void lu_solve_vec(const T* __restrict__ A, int lda, int m, const int* perm, T* v,
-                                             T* tmp /* m scratch (shared) */) {
-  constexpr int NB = Blk<T>::NB;
-  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
-  // v <- P v (block-local row interchanges)
-  for (int i = tid; i < m; i += NT) tmp[i] = v[(i / NB) * NB + perm[i]];
-  __syncthreads();
-  for (int i = tid; i < m; i += NT) v[i] = tmp[i];
-  __syncthreads();
-  // L y = v
-  for (int k0 = 0; k0 < m; k0 += NB) {
-    const int kb = min(NB, m - k0);
-    if (tid < 32) {
-      T acc = 0;
-      if (lane < kb) {
-        acc = v[k0 + lane];
-        const T* row = A + (size_t)(k0 + lane) * lda + k0;
-        for (int q = 0; q < lane; ++q) acc += row[q] * v[k0 + q];
-      }
-      __syncwarp();
-      if (lane < kb) v[k0 + lane] = acc;
-    }
-    __syncthreads();
-    for (int i = k0 + kb + tid; i < m; i += NT) {
-      const T* row = A + (size_t)i * lda + k0;
-      T acc = v[i];
-      for (int c = 0; c < kb; ++c) acc -= row[c] * v[k0 + c];
-      v[i] = acc;
-    }
-    __syncthreads();
-  }
-  // U x = y
-  const int last = ((m - 1) / NB) * NB;
-  for (int k0 = last; k0 >= 0; k0 -= NB) {
-    const int kb = min(NB, m - k0);
-    if (tid < 32) {
-      T acc = 0;
-      if (lane < kb) {
-        const T* row = A + (size_t)(k0 + lane) * lda + k0;
-        for (int c = lane; c < kb; ++c) acc += row[c] * v[k0 + c];
-      }
-      __syncwarp();
-      if (lane < kb) v[k0 + lane] = acc;
-    }
-    __syncthreads();
-    for (int i = tid; i < k0; i += NT) {
-      const T* row = A + (size_t)i * lda + k0;
-      T acc = v[i];
-      for (int c = 0; c < kb; ++c) acc -= row[c] * v[k0 + c];
-      v[i] = acc;
-    }
-    __syncthreads();
-  }
-}
-
 }  // namespace lcpb200
