@@ -119,6 +119,11 @@ class Handle:
 _handles = {}
 
 
+def clear_handles():
+    """Drop every cached handle (tests use it to re-plan under a different environment)."""
+    _handles.clear()
+
+
 def get_handle(dtype, n, m, e, device_index):
     key = (dtype, n, m, e, device_index)
     h = _handles.get(key)

@@ -741,6 +741,7 @@ struct FwdArgs {
   T* ws;
   T* Rsave;                   // nullptr or [B,m,m]: R of every scene, for the backward pass
   long long* prof;            // nullptr or [grid][PH_COUNT]
+  int fallback_only;          // 1: solve only the scenes the condensed kernel flagged (status == -100)
 };
 
 template <typename T, int MODE>
@@ -806,6 +807,7 @@ __global__ void __launch_bounds__(512, 1) lcp_forward_kernel(const FwdArgs<T> a)
   const T NANV = nan("");
 
   for (int sc = blockIdx.x; sc < a.B; sc += gridDim.x) {
+    if (a.fallback_only && a.status[sc] != -100) continue;       // solved by lcp_condensed.cuh
     const T* p = a.p + (size_t)sc * n;
     const T* h = a.h + (size_t)sc * m;
     const T* b = e > 0 ? a.b + (size_t)sc * e : nullptr;
@@ -966,6 +968,7 @@ struct BwdArgs {
   T* ws;
   const T* Rsave;             // nullptr (recompute R) or the matrices saved by the forward pass
   long long* prof;
+  const int* skip;            // nullptr or [B]: non-zero = gradients already written by lcp_condensed.cuh
 };
 
 template <typename T, int MODE>
@@ -982,6 +985,7 @@ __global__ void __launch_bounds__(512, 1) lcp_backward_kernel(const BwdArgs<T> a
   auto off = [&](const T* p_) { return (int)(p_ - sb); };
 
   for (int sc = blockIdx.x; sc < a.B; sc += gridDim.x) {
+    if (a.skip && a.skip[sc]) continue;
     prof_start(c);
     bind_scene(c, P, sm, a.Q + (size_t)sc * n * n, a.G + (size_t)sc * m * n,
                e > 0 ? a.A + (size_t)sc * e * n : nullptr, a.F + (size_t)sc * m * m);

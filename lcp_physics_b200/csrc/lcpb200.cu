@@ -10,8 +10,10 @@
 #include "../../include/lcpb200.h"
 #include "lcp_assemble.cuh"
 #include "lcp_launch.h"
+#include "lcp_cond_launch.h"
 
 using namespace lcpb200;
+using cnd::CPlan;
 
 static thread_local std::string g_err;
 static int fail(const std::string& s) { g_err = s; return 1; }
@@ -41,16 +43,21 @@ struct lcpb200_handle_s {
   int dtype, n, m, e, device;
   int num_sms, smem_optin;
   Plan plan;
-  int max_grid;            // resident CTAs (occupancy * SMs)
+  int max_grid;            // resident CTAs (occupancy * SMs) of the dual-form kernels
+  CPlan cplan;             // condensed-KKT kernels (lcp_condensed.cuh); cplan.ok == 0: not available
+  int cond_grid = 0;       // resident CTAs of the condensed kernels
   static const int NSLOT = 2;   // independent workspace slices (one per pipeline stream)
-  void* ws = nullptr;
+  void* ws = nullptr;      // dual-form workspace, grown on demand: ws_ctas CTAs x NSLOT slices
   size_t ws_bytes = 0;
+  int ws_ctas = 0;
+  DevBuf d_flag[NSLOT];    // per-scene "gradients already written" flags of the backward pass
   // host-buffer pipeline state
   cudaStream_t streams[NSLOT] = {nullptr, nullptr};
   DevBuf d_in[7], d_out[6], d_bwd[16];
   long long* prof = nullptr;      // optional per-CTA phase cycle counters [NSLOT*max_grid][PH_COUNT]
   DevBuf d_R;                     // host pipeline: R of every scene, kept for backward_host
-  int retained_B = 0;             // scenes whose inputs/results/R forward_host left on the device
+  int retained_B = 0;             // scenes whose inputs/results forward_host left on the device
+  bool retained_R = false;        // ... and whether R of those scenes is in d_R
 };
 
 static int pad_ld(int cols, int elem_bytes) {
@@ -144,6 +151,52 @@ static int configure_kernels(lcpb200_handle_s* h) {
   return 0;
 }
 
+
+// ------------------------------------------------------------------ condensed-KKT plan (lcp_condensed.cuh)
+#define LCPB200_NS_DISPATCH(NSV, CALL)                                  \
+  ((NSV) == 2 ? CALL(2) : (NSV) == 3 ? CALL(3) : (NSV) == 4 ? CALL(4) : (NSV) == 6 ? CALL(6) : CALL(8))
+
+template <typename T>
+static int make_cplan(lcpb200_handle_s* h) {
+  CPlan& C = h->cplan;
+  memset(&C, 0, sizeof(C));
+  if (getenv("LCPB200_NO_CONDENSED")) return 0;
+  const int n = h->n, m = h->m, e = h->e, N = n + e;
+  if (N > 128 || n > 255 || m > 4 * cnd::NT) return 0;
+  static const int sizes[5] = {2, 3, 4, 6, 8};
+  int NS = 8;
+  for (int k = 4; k >= 0; --k) if (16 * sizes[k] >= N) NS = sizes[k];
+  C.n = n; C.m = m; C.e = e; C.N = N; C.NS = NS; C.NP = 16 * NS;
+  C.pcap = (m + 7) & ~7;
+  const int dyn_max = h->smem_optin - 1024;
+  const int target = NS <= 3 ? 4 : (NS <= 6 ? 2 : 1);           // CTAs per SM the kernels are bounded for
+  // shared memory per SM: 228 KB, 1 KB reserved per resident CTA
+  const int per_cta_target = (228 * 1024) / target - 1024 - 64;
+  cnd::CSmem<T> sm;
+  int best = -1;
+  for (int want = target; want >= 1 && best < 0; --want) {
+    const int lim = std::min(dyn_max, want == target ? per_cta_target : (228 * 1024) / want - 1024 - 64);
+    for (int mult = cnd::CSMAX; mult >= 1; --mult) {            // capacity of W / Fd: mult * pcap elements
+      C.wcap = mult * C.pcap;
+      const size_t bytes = sm.carve(reinterpret_cast<char*>(16), C);
+      if ((long long)bytes <= lim) { best = (int)bytes; break; }
+      if (mult <= 4) break;                                     // the engine's fd = 2 blocks need 4
+    }
+  }
+  if (best < 0) return 0;
+  C.smem_bytes = best;
+  int occ = 0;
+#define CALL_CFG(NSV) cnd::configure_cond_t<T, NSV>(C.smem_bytes, dyn_max, &occ)
+  const cudaError_t ce = LCPB200_NS_DISPATCH(NS, CALL_CFG);
+#undef CALL_CFG
+  if (ce != cudaSuccess) return fail(std::string("condensed kernel configuration: ") + cudaGetErrorString(ce));
+  if (occ < 1) return 0;
+  C.ctas_per_sm = occ;
+  h->cond_grid = occ * h->num_sms;
+  C.ok = 1;
+  return 0;
+}
+
 extern "C" int lcpb200_version(void) { return LCPB200_VERSION; }
 extern "C" const char* lcpb200_last_error_string(void) { return g_err.c_str(); }
 
@@ -165,11 +218,24 @@ extern "C" int lcpb200_create(int dtype, int n, int m, int e, int device, lcpb20
   int rc = (dtype == LCPB200_F32) ? make_plan<float>(h) : make_plan<double>(h);
   if (!rc) rc = (dtype == LCPB200_F32) ? configure_kernels<float>(h) : configure_kernels<double>(h);
   if (rc) { delete h; return rc; }
-  const size_t esz = dtype == LCPB200_F32 ? 4 : 8;
-  h->ws_bytes = (size_t)h->plan.ws_per_cta * esz * (size_t)h->max_grid * lcpb200_handle_s::NSLOT;
-  ce = cudaMalloc(&h->ws, h->ws_bytes);
-  if (ce != cudaSuccess) { delete h; return fail(std::string("cudaMalloc(workspace): ") + cudaGetErrorString(ce)); }
+  if (!rc) rc = (dtype == LCPB200_F32) ? make_cplan<float>(h) : make_cplan<double>(h);
+  if (rc) { delete h; return rc; }
   *out = h;
+  return 0;
+}
+
+// The dual-form kernels keep U12 / ELL copies / small blocks in a per-CTA L2 workspace. It is sized
+// for the CTAs a call can actually use (min(B, resident CTAs)) and grown on demand, so that a
+// batch-of-one engine call on a large scene does not allocate 148 CTAs' worth.
+static int ensure_ws(lcpb200_handle_s* h, int B) {
+  const int ctas = std::min(B, h->max_grid);
+  if (ctas <= h->ws_ctas) return 0;
+  const size_t esz = h->dtype == LCPB200_F32 ? 4 : 8;
+  const size_t need = (size_t)h->plan.ws_per_cta * esz * (size_t)ctas * lcpb200_handle_s::NSLOT;
+  if (h->ws) { CK(cudaDeviceSynchronize()); CK(cudaFree(h->ws)); h->ws = nullptr; h->ws_bytes = 0; h->ws_ctas = 0; }
+  CK(cudaMalloc(&h->ws, need));
+  h->ws_bytes = need;
+  h->ws_ctas = ctas;
   return 0;
 }
 
@@ -182,6 +248,7 @@ extern "C" int lcpb200_destroy(lcpb200_handle_t h) {
   for (auto& b : h->d_in) b.release();
   for (auto& b : h->d_out) b.release();
   for (auto& b : h->d_bwd) b.release();
+  for (auto& b : h->d_flag) b.release();
   h->d_R.release();
   delete h;
   return 0;
@@ -193,10 +260,18 @@ extern "C" int lcpb200_describe(lcpb200_handle_t h, char* buf, size_t len) {
   if (!h || !buf) return fail("null argument");
   const Plan& P = h->plan;
   static const char* modes[3] = {"smem", "smem-split(U12 in L2)", "L2"};
+  const CPlan& C = h->cplan;
+  char cbuf[256];
+  if (C.ok)
+    snprintf(cbuf, sizeof(cbuf), "condensed KKT: N=%d(pad %d) fp64 LU in registers, threads=%d smem=%dB CTAs/SM=%d grid<=%d "
+             "(forward%s; unstructured scenes fall back to dual)", C.N, C.NP, cnd::NT, C.smem_bytes, C.ctas_per_sm,
+             h->cond_grid, h->dtype == LCPB200_F32 ? "+backward" : "");
+  else
+    snprintf(cbuf, sizeof(cbuf), "condensed KKT: n/a");
   snprintf(buf, len,
-           "dtype=%s n=%d m=%d(pad %d) e=%d threads=%d smem=%dB T:%s m1=%d ldT=%d ldL=%d G:%s Qinv:%s grid<=%d "
+           "dtype=%s n=%d m=%d(pad %d) e=%d | %s | dual: threads=%d smem=%dB T:%s m1=%d ldT=%d ldL=%d G:%s Qinv:%s grid<=%d "
            "ws/CTA=%lldB sms=%d",
-           h->dtype == LCPB200_F32 ? "f32" : "f64", P.n, P.m, P.mp, P.e, P.nt, P.smem_bytes, modes[P.mode], P.m1,
+           h->dtype == LCPB200_F32 ? "f32" : "f64", P.n, P.m, P.mp, P.e, cbuf, P.nt, P.smem_bytes, modes[P.mode], P.m1,
            P.ldT, P.ldL, P.G_smem ? "smem" : "L2", P.Qi_smem ? "smem" : "L2", h->max_grid,
            (long long)(P.ws_per_cta * (h->dtype == LCPB200_F32 ? 4 : 8)), h->num_sms);
   return 0;
@@ -207,6 +282,25 @@ static int launch_forward(lcpb200_handle_s* h, int slot, int B, const void* Q, c
                           const void* hv, const void* A, const void* b, const void* F, double eps,
                           int not_improved_lim, int max_iter, void* zhat, void* nu, void* lam, void* slack,
                           int32_t* status, int32_t* iters, void* resid, void* Rsave, cudaStream_t st) {
+  const bool cond = h->cplan.ok != 0;
+  if (cond) {
+    // structured scenes: condensed-KKT kernel; it flags the others (status = -100) for the dual-form kernel below
+    cnd::CFwdArgs<T> c;
+    c.P = h->cplan;
+    c.B = B;
+    c.Q = (const T*)Q; c.p = (const T*)p; c.G = (const T*)G; c.h = (const T*)hv;
+    c.A = (const T*)A; c.b = (const T*)b; c.F = (const T*)F;
+    c.zhat = (T*)zhat; c.nu = (T*)nu; c.lam = (T*)lam; c.slack = (T*)slack; c.resid = (T*)resid;
+    c.status = status; c.iters = iters;
+    c.eps = (T)eps; c.not_improved_lim = not_improved_lim; c.max_iter = max_iter;
+    const int cgrid = std::min(B, h->cond_grid);
+#define CALL_FWD(NSV) cnd::launch_cond_forward_t<T, NSV>(c, cgrid, st)
+    const cudaError_t ce = LCPB200_NS_DISPATCH(h->cplan.NS, CALL_FWD);
+#undef CALL_FWD
+    CK(ce);
+    Rsave = nullptr;          // the condensed kernel does not form R; the dual-form backward recomputes it
+  }
+  if (int rc = ensure_ws(h, B)) return rc;
   FwdArgs<T> a;
   a.P = h->plan;
   a.B = B;
@@ -216,9 +310,10 @@ static int launch_forward(lcpb200_handle_s* h, int slot, int B, const void* Q, c
   a.status = status; a.iters = iters;
   a.eps = (T)eps; a.not_improved_lim = not_improved_lim; a.max_iter = max_iter;
   a.Rsave = (T*)Rsave;
-  a.ws = (T*)h->ws + (size_t)slot * h->plan.ws_per_cta * h->max_grid;
+  a.fallback_only = cond ? 1 : 0;
+  a.ws = (T*)h->ws + (size_t)slot * h->plan.ws_per_cta * h->ws_ctas;
   a.prof = h->prof ? h->prof + (size_t)slot * h->max_grid * PH_COUNT : nullptr;
-  const int grid = std::min(B, h->max_grid);
+  const int grid = std::min(B, h->ws_ctas);
   const int mode = h->plan.mode;
   const cudaError_t le = mode == 0   ? launch_forward_t<T, 0>(a, grid, st)
                          : mode == 1 ? launch_forward_t<T, 1>(a, grid, st)
@@ -232,6 +327,28 @@ static int launch_backward(lcpb200_handle_s* h, int slot, int B, const void* Q, 
                            const void* F, const void* zhat, const void* nu, const void* lam, const void* slack,
                            const void* g, void* dQ, void* dp, void* dG, void* dh, void* dA, void* db, void* dF,
                            const void* Rsave, unsigned flags, cudaStream_t st) {
+  // fp32: condensed-KKT backward first. fp64 stays on the dual form: at the fp64 round-off floor
+  // (lambda, s ~ 1e-16, d = lambda/s spanning 1e+-16) the condensed matrix loses dx (DESIGN.md "Parity").
+  const bool cond = h->cplan.ok != 0 && sizeof(T) == 4 && !getenv("LCPB200_DUAL_BACKWARD");
+  int* done = nullptr;
+  if (cond) {
+    CK(h->d_flag[slot].ensure(sizeof(int) * (size_t)B));
+    done = (int*)h->d_flag[slot].p;
+    cnd::CBwdArgs<T> c;
+    c.P = h->cplan;
+    c.B = B;
+    c.Q = (const T*)Q; c.G = (const T*)G; c.A = (const T*)A; c.F = (const T*)F;
+    c.zhat = (const T*)zhat; c.nu = (const T*)nu; c.lam = (const T*)lam; c.slack = (const T*)slack;
+    c.g = (const T*)g;
+    c.dQ = (T*)dQ; c.dp = (T*)dp; c.dG = (T*)dG; c.dh = (T*)dh; c.dA = (T*)dA; c.db = (T*)db; c.dF = (T*)dF;
+    c.done = done;
+    const int cgrid = std::min(B, h->cond_grid);
+#define CALL_BWD(NSV) cnd::launch_cond_backward_t<T, NSV>(c, cgrid, st)
+    const cudaError_t ce = LCPB200_NS_DISPATCH(h->cplan.NS, CALL_BWD);
+#undef CALL_BWD
+    CK(ce);
+  }
+  if (int rc = ensure_ws(h, B)) return rc;
   BwdArgs<T> a;
   a.P = h->plan;
   a.B = B;
@@ -240,10 +357,11 @@ static int launch_backward(lcpb200_handle_s* h, int slot, int B, const void* Q, 
   a.g = (const T*)g;
   a.dQ = (T*)dQ; a.dp = (T*)dp; a.dG = (T*)dG; a.dh = (T*)dh; a.dA = (T*)dA; a.db = (T*)db; a.dF = (T*)dF;
   a.flags = flags;
-  a.Rsave = (const T*)Rsave;
-  a.ws = (T*)h->ws + (size_t)slot * h->plan.ws_per_cta * h->max_grid;
+  a.Rsave = (h->cplan.ok != 0) ? nullptr : (const T*)Rsave;    // R is only formed when the forward ran on the dual form
+  a.skip = done;
+  a.ws = (T*)h->ws + (size_t)slot * h->plan.ws_per_cta * h->ws_ctas;
   a.prof = h->prof ? h->prof + (size_t)slot * h->max_grid * PH_COUNT : nullptr;
-  const int grid = std::min(B, h->max_grid);
+  const int grid = std::min(B, h->ws_ctas);
   const int mode = h->plan.mode;
   const cudaError_t le = mode == 0   ? launch_backward_t<T, 0>(a, grid, st)
                          : mode == 1 ? launch_backward_t<T, 1>(a, grid, st)
@@ -355,7 +473,8 @@ extern "C" int lcpb200_forward_host(lcpb200_handle_t h, int B, const void* Q, co
   DevBuf& d_resid = h->d_bwd[15];
   if (resid) CK(d_resid.ensure(w * B));
   h->retained_B = 0;
-  const bool keepR = (m * m * w * (size_t)B) <= ((size_t)8 << 30);      // keep R for backward_host (<= 8 GiB)
+  // keep R for backward_host (<= 8 GiB) -- only the dual-form forward produces it
+  const bool keepR = !h->cplan.ok && (m * m * w * (size_t)B) <= ((size_t)8 << 30);
   if (keepR) CK(h->d_R.ensure(m * m * w * (size_t)B));
   const int C = chunk_scenes(h, B);
   int k = 0;
@@ -394,7 +513,8 @@ extern "C" int lcpb200_forward_host(lcpb200_handle_t h, int B, const void* Q, co
       CK(cudaMemcpyAsync((char*)resid + w * s0, (char*)d_resid.p + w * s0, w * cb, cudaMemcpyDeviceToHost, st));
   }
   for (auto& s : h->streams) CK(cudaStreamSynchronize(s));
-  h->retained_B = keepR ? B : 0;
+  h->retained_B = B;
+  h->retained_R = keepR;
   return 0;
 }
 
@@ -449,7 +569,7 @@ extern "C" int lcpb200_backward_host(lcpb200_handle_t h, int B, const void* Q, c
     auto ai = [&](int i) -> void* {
       return (in_sz[i] && (in_src[i] || resident[i])) ? (char*)in_buf[i]->p + in_sz[i] * s0 : nullptr;
     };
-    const void* rs = retained ? (const char*)h->d_R.p + m * m * w * s0 : nullptr;
+    const void* rs = (retained && h->retained_R) ? (const char*)h->d_R.p + m * m * w * s0 : nullptr;
     auto ao = [&](int i) -> void* { return (out_sz[i] && out_dst[i]) ? (char*)out_buf[i]->p + out_sz[i] * s0 : nullptr; };
     int rc = h->dtype == LCPB200_F32
                  ? launch_backward<float>(h, slot, cb, ai(0), ai(1), ai(2), ai(3), ai(4), ai(5), ai(6), ai(7), ai(8),

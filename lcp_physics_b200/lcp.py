@@ -62,9 +62,8 @@ def solve_forward(Q, p, G, h, A, b, F, eps=1e-12, not_improved_lim=3, max_iter=1
     """Raw forward: returns (zhat, nus, lams, slacks, status, iters, resid).
     All inputs on one device (CUDA or CPU), same dtype. `out` may hold preallocated
     result tensors (same order; pinned host tensors make the host path's D2H fast).
-    `save`: a dict that receives what the backward can reuse -- for CUDA inputs the
-    per-scene Schur matrix R ("R"); for CPU inputs a token of the state the library
-    retained on the device ("token")."""
+    `save`: a dict that receives what the backward can reuse -- for CPU inputs a token
+    of the state the library retained on the device ("token")."""
     _lib.require_cuda()
     lib = _lib.load()
     B, n, m, e = _sizes(Q, p, G, h, A, b, F)
@@ -96,14 +95,8 @@ def solve_forward(Q, p, G, h, A, b, F, eps=1e-12, not_improved_lim=3, max_iter=1
         if save is not None:
             save["token"] = (hd, hd.host_generation, B)
     else:
-        R = None
-        if save is not None and B * m * m * Q.element_size() <= (8 << 30):
-            R = save.get("R_buffer")
-            if R is None or R.shape != (B, m, m) or R.dtype != dtype or R.device != dev:
-                R = torch.empty(B, m, m, dtype=dtype, device=dev)
-            save["R"] = R
         with torch.cuda.device(dev):
-            _lib.check(lib.lcpb200_forward(*args, _lib.ptr(R), _stream_ptr(dev)))
+            _lib.check(lib.lcpb200_forward(*args, None, _stream_ptr(dev)))
     return zhat, nu, lam, slack, status, iters, resid
 
 
@@ -142,8 +135,7 @@ def solve_backward(Q, G, A, F, zhat, nu, lam, slack, dl_dzhat, need=(True,) * 7,
         hd.host_generation += 1
         _lib.check(lib.lcpb200_backward_host(hd.raw, B, *in_ptrs, *[_lib.ptr(t) for t in outs], 0))
     else:
-        R = saved.get("R") if saved else None
-        args = [hd.raw, B] + [_lib.ptr(t) for t in ins] + [_lib.ptr(t) for t in outs] + [_lib.ptr(R), 0]
+        args = [hd.raw, B] + [_lib.ptr(t) for t in ins] + [_lib.ptr(t) for t in outs] + [None, 0]
         with torch.cuda.device(dev):
             _lib.check(lib.lcpb200_backward(*args, _stream_ptr(dev)))
     return tuple(outs)
