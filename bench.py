@@ -44,6 +44,10 @@ MAX_ITER = 10
 METRIC = "LCP solves/sec (LCPFunction fwd+bwd, batch=4096 x 64 contacts, fp32)"
 UNIT = "solves/s"
 
+# BASELINE.json configs[1] (--config cfg2): LCPFunction forward only, batch=1024, 32 contacts, 3 friction dirs, fp64
+CFG2 = dict(nb=16, nc=32, fd=3, e=0, batch=1024)
+METRIC_CFG2 = "LCP solves/sec (LCPFunction forward only, batch=1024 x 32 contacts x 3 fric dirs, fp64)"
+
 
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -52,6 +56,21 @@ def load_peaks():
             d = json.load(f)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# FP32 / FP64 FMA pipe peaks measured on this pool with scripts/ubench/pipes.cu (record:
+# profiles/r02_ubench_pipes_latencies.txt): FFMA 70.5 TFLOP/s (121 FMA/clk/SM), DFMA 36.6 TFLOP/s (63 FMA/clk/SM)
+FFMA_PEAK_TFLOPS = 70.5
+DFMA_PEAK_TFLOPS = 36.6
+
+
+def condensed_fp64_flops(n, m_blocks, cs, ucols, iters_mean):
+    """FP64 flops the condensed-KKT kernel needs per solve: per factorisation an n x n LU
+    (2/3 n^3), the block inverses (2 cs^3 each) and the assembly of K (2 cs^2 ucols + 2 cs ucols^2 per block);
+    per solve two triangular substitutions (2 n^2) and two block mat-vecs. K + 1 factorisations, 2K + 1 solves."""
+    fact = 2.0 / 3 * n ** 3 + m_blocks * (2.0 * cs ** 3 + 2.0 * cs * cs * ucols + 2.0 * cs * ucols * ucols)
+    solve = 2.0 * n * n + m_blocks * (4.0 * cs * cs + 4.0 * cs * ucols)
+    return (iters_mean + 1) * fact + (2 * iters_mean + 1) * solve
 
 
 def algorithmic(n, m, e, w, iters_mean):
@@ -117,18 +136,20 @@ def use_all_host_threads():
     return torch.get_num_threads()
 
 
-def cpu_reference_leg(B_sample, dtype, seed, reps=1):
-    """Oracle port of the reference CPU path (as-is semantics), fwd+bwd on B_sample scenes."""
+def cpu_reference_leg(B_sample, dtype, seed, reps=1, cfg2=False):
+    """Oracle port of the reference CPU path (as-is semantics) on B_sample scenes: fwd+bwd (cfg3) or forward (cfg2)."""
     from oracle import pdipm_oracle as po
     from lcp_physics_b200.scenes import make_scenes
-    inp = make_scenes(B_sample, NB, NC, fd=FD, e=NEQ, dtype=dtype, seed=seed)
-    g = torch.randn(B_sample, N_DOF, dtype=dtype, generator=torch.Generator().manual_seed(seed))
+    nb, nc, fd, e = (CFG2["nb"], CFG2["nc"], CFG2["fd"], CFG2["e"]) if cfg2 else (NB, NC, FD, NEQ)
+    inp = make_scenes(B_sample, nb, nc, fd=fd, e=e, dtype=dtype, seed=seed)
+    g = torch.randn(B_sample, 3 * nb, dtype=dtype, generator=torch.Generator().manual_seed(seed))
     small = tuple(t[:4] if t.dim() > 1 else t for t in inp)
     po.lcp_backward(po.lcp_forward(*small, max_iter=MAX_ITER, unpack="loop"), g[:4])   # warm-up
     t0 = time.perf_counter()
     for _ in range(reps):
         res = po.lcp_forward(*inp, max_iter=MAX_ITER, unpack="loop")
-        po.lcp_backward(res, g)
+        if not cfg2:
+            po.lcp_backward(res, g)
     dt = (time.perf_counter() - t0) / reps
     return B_sample / dt, dt
 
@@ -138,27 +159,71 @@ def run_reference(args, rank, world):
         return
     cores = use_all_host_threads()
     Bs = args.ref_batch
+    cfg2 = args.config == "cfg2"
+    rdt = torch.float64 if cfg2 else torch.float32
+    full_batch = args.batch or (CFG2["batch"] if cfg2 else 4096)
     for _ in range(args.warmup and 1):
-        cpu_reference_leg(8, torch.float32, 1)
+        cpu_reference_leg(8, rdt, 1, cfg2=cfg2)
     t0 = time.perf_counter()
     for k in range(args.steps):
-        cpu_reference_leg(Bs, torch.float32, 100 + k)
+        cpu_reference_leg(Bs, rdt, 100 + k, cfg2=cfg2)
     dt = time.perf_counter() - t0
     val = Bs * args.steps / dt
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "impl": "reference", "metric": METRIC_CFG2 if cfg2 else METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD % args.batch, "global_batch": world * args.batch,
+        "vs_baseline": None, "dtype": "f64" if cfg2 else "f32", "data": "synthetic",
+        "config": {"workload": (METRIC_CFG2 if cfg2 else WORKLOAD % full_batch), "global_batch": world * full_batch,
                    "parallelism": "host CPU, rank 0 only", "sample_batch": Bs,
                    "note": "each step times a bounded sample of the workload (sample_batch scenes) on the host cores"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d scenes per step (of the 4096-scene batch), fwd+bwd, as-is reference "
-                                   "semantics incl. util.py:86-90 pivot loop" % Bs},
+                         "sample": "%d scenes per step (of the %d-scene batch), %s, as-is reference "
+                                   "semantics incl. util.py:86-90 pivot loop" % (Bs, full_batch, "forward" if cfg2 else "fwd+bwd")},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def parity_sample(inp_host, g_host, fo_dev, bo_dev, n_sample, dtype, max_iter, with_backward):
+    """Real parity on the first n_sample scenes of the TIMED batch (rank 0): the oracle port of the reference in
+    the run's dtype (the reference's own answer) and in fp64 (the truth), against what the GPU returned.
+    Also returns the CPU timing of the as-is oracle run (the cpu_baseline of the same scenes)."""
+    from oracle import pdipm_oracle as po
+    sub = tuple(t[:n_sample].clone() if t.dim() > 1 else t for t in inp_host)
+    g = g_host[:n_sample]
+    t0 = time.perf_counter()
+    res = po.lcp_forward(*sub, max_iter=max_iter, unpack="loop")          # as-is reference semantics
+    rg = po.lcp_backward(res, g) if with_backward else None
+    dt = time.perf_counter() - t0
+    sub64 = tuple(t.double() for t in sub)
+    res64 = po.lcp_forward(*sub64, max_iter=max_iter)
+
+    def rel(a, b_):
+        a = a.double().reshape(a.shape[0], -1); b_ = b_.double().reshape(b_.shape[0], -1)
+        return (a - b_).norm(dim=1) / b_.norm(dim=1).clamp_min(1e-300)
+
+    def stats(e):
+        return {"frac_within_tol": float((e < TOL[dtype]).float().mean()), "median": float(e.median()),
+                "p90": float(e.quantile(0.9)), "max": float(e.max())}
+
+    z = fo_dev[0][:n_sample].cpu()
+    out = {"n": n_sample, "tol": TOL[dtype],
+           "zhat_vs_reference": stats(rel(z, res.zhat)),
+           "zhat_vs_fp64": stats(rel(z, res64.zhat)),
+           "reference_vs_fp64": stats(rel(res.zhat, res64.zhat))}
+    if with_backward:
+        # gradient truth: the fp64 oracle on the state the GPU forward returned (the backward map itself)
+        st = [None if t is None else t[:n_sample].double().cpu() for t in (fo_dev[0], fo_dev[1], fo_dev[2], fo_dev[3])]
+        truth = po.lcp_backward_from_saved(sub64, st[0], st[1], st[2], st[3], g.double())
+        out["dp_vs_fp64_same_state"] = stats(rel(bo_dev[1][:n_sample].cpu(), truth[1]))
+        out["dQ_vs_fp64_same_state"] = stats(rel(bo_dev[0][:n_sample].cpu(), truth[0]))
+        out["dG_vs_fp64_same_state"] = stats(rel(bo_dev[2][:n_sample].cpu(), truth[2]))
+        out["reference_dp_vs_fp64_own_state"] = stats(rel(rg[1], po.lcp_backward(res64, g.double())[1]))
+    return out, n_sample / dt, dt
+
+
+TOL = {torch.float32: 1e-3, torch.float64: 1e-6}
 
 
 def run_b200(args, rank, world, local_rank):
@@ -170,29 +235,39 @@ def run_b200(args, rank, world, local_rank):
     _lib.require_cuda()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    B = args.batch
-    dtype = torch.float32
-    w = 4
+    cfg2 = args.config == "cfg2"
+    if cfg2:
+        nb, nc, fd, neq = CFG2["nb"], CFG2["nc"], CFG2["fd"], CFG2["e"]
+        B = args.batch or CFG2["batch"]
+        dtype, w, with_bwd, metric = torch.float64, 8, False, METRIC_CFG2
+        workload = ("LCPFunction forward only, batch=%d scenes/GPU x 32 contacts x 3 fric dirs (n=48, m=160, neq=0), "
+                    "fp64, max_iter=10, pile scenes (lcp_physics_b200/scenes.py)" % B)
+    else:
+        nb, nc, fd, neq = NB, NC, FD, NEQ
+        B = args.batch or 4096
+        dtype, w, with_bwd, metric = torch.float32, 4, True, METRIC
+        workload = WORKLOAD % B
+    n_dof, m_ineq = 3 * nb, nc * (2 + fd)
 
-    inp_host = make_scenes(B, NB, NC, fd=FD, e=NEQ, dtype=dtype, seed=1000 + rank)
-    g_host = torch.randn(B, N_DOF, dtype=dtype, generator=torch.Generator().manual_seed(rank))
+    inp_host = make_scenes(B, nb, nc, fd=fd, e=neq, dtype=dtype, seed=1000 + rank)
+    g_host = torch.randn(B, n_dof, dtype=dtype, generator=torch.Generator().manual_seed(rank))
     inp = tuple(t.to(dev) for t in inp_host)
     g = g_host.to(dev)
     Q, p, G, h, A, b, F = inp
 
     def mk_fwd_out(device, pin=False):
         kw = dict(device=device, pin_memory=pin)
-        return (torch.empty(B, N_DOF, dtype=dtype, **kw), None, torch.empty(B, M_INEQ, dtype=dtype, **kw),
-                torch.empty(B, M_INEQ, dtype=dtype, **kw), torch.empty(B, dtype=torch.int32, **kw),
+        return (torch.empty(B, n_dof, dtype=dtype, **kw), None, torch.empty(B, m_ineq, dtype=dtype, **kw),
+                torch.empty(B, m_ineq, dtype=dtype, **kw), torch.empty(B, dtype=torch.int32, **kw),
                 torch.empty(B, dtype=torch.int32, **kw), torch.empty(B, dtype=dtype, **kw))
 
     def mk_bwd_out(device, pin=False):
         kw = dict(device=device, pin_memory=pin, dtype=dtype)
-        return (torch.empty(B, N_DOF, N_DOF, **kw), torch.empty(B, N_DOF, **kw), torch.empty(B, M_INEQ, N_DOF, **kw),
-                torch.empty(B, M_INEQ, **kw), None, None, torch.empty(B, M_INEQ, M_INEQ, **kw))
+        return (torch.empty(B, n_dof, n_dof, **kw), torch.empty(B, n_dof, **kw), torch.empty(B, m_ineq, n_dof, **kw),
+                torch.empty(B, m_ineq, **kw), None, None, torch.empty(B, m_ineq, m_ineq, **kw))
 
-    fo, bo = mk_fwd_out(dev), mk_bwd_out(dev)
-    saved = {"R_buffer": torch.empty(B, M_INEQ, M_INEQ, dtype=dtype, device=dev)}   # the reference's self.R (lcp.py:28)
+    fo = mk_fwd_out(dev)
+    bo = mk_bwd_out(dev) if with_bwd else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kev = []
 
@@ -200,14 +275,15 @@ def run_b200(args, rank, world, local_rank):
         if record:
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record()
-        solve_forward(Q, p, G, h, A, b, F, max_iter=MAX_ITER, out=fo, save=saved)
+        solve_forward(Q, p, G, h, A, b, F, max_iter=MAX_ITER, out=fo)
         if record:
             e1.record()
-        solve_backward(Q, G, A, F, fo[0], None, fo[2], fo[3], g, out=bo, saved=saved)
+        if with_bwd:
+            solve_backward(Q, G, A, F, fo[0], None, fo[2], fo[3], g, out=bo)
         if record:
             e2.record()
             kev.append((e0, e1, e2))
-        if world > 1:
+        if world > 1 and with_bwd:
             # the path's only exchange: gather per-rank loss gradients (here d loss / d p and d h summed over scenes)
             local = torch.cat([bo[1].sum(0), bo[3].sum(0)])
             gather_loss_gradients(local)
@@ -237,19 +313,20 @@ def run_b200(args, rank, world, local_rank):
     fwd_ms = sum(a.elapsed_time(b_) for a, b_, _ in kev) / len(kev)
     bwd_ms = sum(b_.elapsed_time(c) for _, b_, c in kev) / len(kev)
     iters_mean = fo[5].float().mean().item()
-    ok = bool(torch.isfinite(fo[0]).all()) and bool((fo[4] >= 0).all())
+    finite_ok = bool(torch.isfinite(fo[0]).all()) and bool((fo[4] >= 0).all())
 
     # ---- e2e: public API with pinned host buffers (H2D inputs + D2H results inside the timed region)
     pin = lambda t_: t_.pin_memory() if t_.numel() else t_
     hin = tuple(pin(t_) for t_ in inp_host)
     hg = pin(g_host)
-    hfo, hbo = mk_fwd_out("cpu", pin=True), mk_bwd_out("cpu", pin=True)
-
+    hfo = mk_fwd_out("cpu", pin=True)
+    hbo = mk_bwd_out("cpu", pin=True) if with_bwd else None
     hsaved = {}
 
     def e2e_step():
         solve_forward(*hin, max_iter=MAX_ITER, out=hfo, save=hsaved)
-        solve_backward(hin[0], hin[2], hin[4], hin[6], hfo[0], None, hfo[2], hfo[3], hg, out=hbo, saved=hsaved)
+        if with_bwd:
+            solve_backward(hin[0], hin[2], hin[4], hin[6], hfo[0], None, hfo[2], hfo[3], hg, out=hbo, saved=hsaved)
 
     e2e_steps = max(1, min(args.steps, 3))
     e2e_step()
@@ -264,54 +341,77 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = t.item()
     in_bytes = sum(t_.numel() * w for t_ in inp_host)
-    h2d = in_bytes + N_DOF * w * B                          # the 7 inputs once (kept on the device) + dl_dzhat
-    d2h = ((N_DOF + 2 * M_INEQ + 1) * w + 8) * B + in_bytes  # zhat, lam, slack, resid, status, iters + the 7 gradients
+    h2d = in_bytes + (n_dof * w * B if with_bwd else 0)     # the 7 inputs once (kept on the device) + dl_dzhat
+    d2h = ((n_dof + 2 * m_ineq + 1) * w + 8) * B + (in_bytes if with_bwd else 0)   # zhat, lam, slack, resid, status, iters (+ the 7 gradients)
 
     if rank != 0:
         return
-    alg = algorithmic(N_DOF, M_INEQ, NEQ, w, iters_mean)
+    alg = algorithmic(n_dof, m_ineq, neq, w, iters_mean)
     peak, peak_src = load_peaks()
     stream_gbs = alg["b_fwd_stream"] * B / (fwd_ms * 1e-3) / 1e9
-    fma_peak = 70.3       # TFLOP/s FP32 FFMA measured on this pool (scripts/ubench/pipes.cu); nominal 74.5 at 1965 MHz
+    dense_tflops = alg["W_fwd"] * B / (fwd_ms * 1e-3) / 1e12
+    fma_peak = DFMA_PEAK_TFLOPS if cfg2 else FFMA_PEAK_TFLOPS
+    c64 = condensed_fp64_flops(n_dof, nc, 2 + fd, 6, iters_mean) * B / (fwd_ms * 1e-3) / 1e12
+    step_bytes = alg["b_fwd_resident"] + (alg["b_bwd"] if with_bwd else 0)
+    kern = "cond_forward_kernel<%s, %d>" % ("double" if cfg2 else "float", 3 if cfg2 else 6)
     line = {
-        "metric": METRIC, "value": world * B * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+        "metric": metric, "value": world * B * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD % B,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if cfg2 else "f32 I/O and iterates; the condensed n x n KKT matrix is formed, factored and solved in f64",
+        "data": "synthetic",
+        "config": {"workload": workload,
                    "global_batch": world * B, "parallelism": "scene-sharded x%d" % world,
-                   "l2": "inputs+gradients per step (3.3 GB) exceed the 126 MB L2, no flush needed",
-                   "mean_pdipm_iters": iters_mean, "parity_ok": ok},
+                   "l2": "inputs%s per step (%.1f GB) exceed the 126 MB L2, no flush needed"
+                         % (" + gradients" if with_bwd else "", step_bytes * B / 1e9),
+                   "mean_pdipm_iters": iters_mean, "finite_ok": finite_ok},
         "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "api": "solve_forward/solve_backward on pinned CPU tensors -> lcpb200_forward_host/backward_host"},
-        "gpu_launches": 2 * args.steps,
-        "kernels": {"lcp_forward_kernel<float>_ms": fwd_ms, "lcp_backward_kernel<float>_ms": bwd_ms},
-        "roofline": {"bound": "hbm", "kernel": "lcp_forward_kernel<float>",
-                     "achieved": stream_gbs, "peak": peak, "unit": "GB/s", "frac": stream_gbs / peak,
-                     "traffic": measured_traffic(B), "peak_source": peak_src,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one forward launch, ncu --set full "
-                                       "(profiles/*_fwd_traffic.json), scaled by batch",
-                     "definition": "north_star per-iteration HBM roofline: (K+1) x (m^2+mn+n^2) x 4 B per solve "
-                                   "(the KKT block streamed once per factorisation) / forward-kernel time",
-                     "resident_bytes_gbs": alg["b_fwd_resident"] * B / (fwd_ms * 1e-3) / 1e9,
-                     "fma": {"achieved_tflops": alg["W_fwd"] * B / (fwd_ms * 1e-3) / 1e12, "peak_tflops": fma_peak,
-                             "frac": alg["W_fwd"] * B / (fwd_ms * 1e-3) / 1e12 / fma_peak,
-                             "note": "dense-formulation flops (SURVEY 8d) / measured FFMA peak; the kernel is latency-bound on the LU pivot chain (DESIGN.md 3.4)"}},
+                "api": "solve_forward%s on pinned CPU tensors -> lcpb200_forward_host%s"
+                       % (("/solve_backward", "/backward_host") if with_bwd else ("", "")),
+                "pcie_note": "dense host tensors: %.2f GB H2D + %.2f GB D2H per step bound this number, not the kernels"
+                             % (h2d / 1e9, d2h / 1e9)},
+        "gpu_launches": (4 if with_bwd else 2) * args.steps,
+        "kernels": {"forward_ms (cond_forward_kernel + dual-form fallback launch)": fwd_ms,
+                    "backward_ms (cond_backward_kernel + dual-form fallback launch)": bwd_ms if with_bwd else None},
+        "roofline": {"bound": "fma", "kernel": kern,
+                     "achieved": dense_tflops, "peak": fma_peak, "unit": "TFLOP/s", "frac": dense_tflops / fma_peak,
+                     "traffic": measured_traffic(B, "cfg2" if cfg2 else "cfg3"),
+                     "peak_source": "%s FMA pipe measured on this pool (scripts/ubench/pipes.cu, profiles/r02_ubench_pipes_latencies.txt)"
+                                    % ("FP64" if cfg2 else "FP32"),
+                     "definition": "ALGORITHMIC flops of the reference's dense dual formulation (SURVEY 8d: W_fwd, %.1f MFLOP/solve "
+                                   "at the measured iteration count) / forward time / the FMA-pipe peak of the I/O dtype. The kernel "
+                                   "reaches the same iterates through the condensed n x n system in fp64 and executes far fewer flops; "
+                                   "see fp64_pipe for the executed work" % (alg["W_fwd"] / 1e6),
+                     "fp64_pipe": {"achieved_tflops": c64, "peak_tflops": DFMA_PEAK_TFLOPS, "frac": c64 / DFMA_PEAK_TFLOPS,
+                                   "note": "necessary fp64 flops of the condensed formulation (LU 2/3 n^3 per factorisation + block "
+                                           "inverses + assembly + substitutions) / forward time / measured DFMA peak"},
+                     "hbm_per_iteration": {"achieved_gbs": stream_gbs, "peak_gbs": peak, "frac": stream_gbs / peak,
+                                           "peak_source": peak_src,
+                                           "definition": "north_star per-iteration HBM roofline: (K+1) x (m^2+mn+n^2) x w bytes per "
+                                                         "solve (the dense KKT block streamed once per factorisation) / forward time"},
+                     "hbm_resident": {"achieved_gbs": alg["b_fwd_resident"] * B / (fwd_ms * 1e-3) / 1e9, "peak_gbs": peak,
+                                      "definition": "every input read once, every output written once / forward time"}},
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
         ncores = use_all_host_threads()
-        val, dt = cpu_reference_leg(args.cpu_sample, dtype, 7)
+        par, val, dt = parity_sample(inp_host, g_host, fo, bo, args.cpu_sample, dtype, MAX_ITER, with_bwd)
+        line["parity"] = par
+        line["config"]["parity_ok"] = bool(par["zhat_vs_reference"]["frac_within_tol"] >= 0.9 and
+                                           par["zhat_vs_fp64"]["p90"] <= 1.2 * par["reference_vs_fp64"]["p90"] + 1e-5)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": ncores, "kind": "port",
-                                "sample": "%d of the 4096 scenes, fwd+bwd, %.1f s, as-is reference semantics "
-                                          "(incl. util.py:86-90 pivot loop)" % (args.cpu_sample, dt)}
+                                "sample": "the first %d scenes of the timed batch, %s, %.1f s, as-is reference semantics "
+                                          "(incl. util.py:86-90 pivot loop); the same scenes feed `parity`"
+                                          % (args.cpu_sample, "fwd+bwd" if with_bwd else "forward", dt)}
     print(json.dumps(line), flush=True)
 
 
-def measured_traffic(batch):
-    """DRAM bytes per forward launch from the newest committed ncu capture (profiles/rNN_fwd_traffic.json)."""
+def measured_traffic(batch, cfg="cfg3"):
+    """DRAM bytes per forward launch from the newest committed ncu capture (profiles/rNN_fwd_traffic[_cfg2].json)."""
     import glob
-    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r*_fwd_traffic.json")))
+    pat = "r*_fwd_traffic.json" if cfg == "cfg3" else "r*_fwd_traffic_cfg2.json"
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", pat)))
     if not files:
         return None
     with open(files[-1]) as f:
@@ -325,7 +425,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="scenes per GPU")
+    ap.add_argument("--config", default="cfg3", choices=["cfg3", "cfg2"],
+                    help="cfg3 (default, BASELINE's headline): fwd+bwd, 4096 x 64 contacts, fp32; "
+                         "cfg2: forward only, 1024 x 32 contacts x 3 fric dirs, fp64")
+    ap.add_argument("--batch", type=int, default=0, help="scenes per GPU (default: the config's)")
     ap.add_argument("--cpu-sample", type=int, default=128)
     ap.add_argument("--ref-batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")

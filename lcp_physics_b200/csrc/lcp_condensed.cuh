@@ -49,19 +49,6 @@ constexpr int KS = 8;            // scan slots per row of F / G
 constexpr int LMAX = 16;         // max (component, slot) entries per column of G
 constexpr int STATUS_UNSUPPORTED = -100;   // internal: scene left to the dual-form kernel
 
-__device__ __forceinline__ double rcp64(double x) {
-  // reciprocal off the slow IEEE-division path: fp32 seed + 3 Newton steps (~1 ulp); exact
-  // division outside the seed's range (also keeps inf / nan semantics)
-  float xf = (float)x, rf;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(xf));
-  if (!(fabsf(rf) < INFINITY) || rf == 0.0f) return 1.0 / x;
-  double r = (double)rf;
-  r = fma(r, fma(-x, r, 1.0), r);
-  r = fma(r, fma(-x, r, 1.0), r);
-  r = fma(r, fma(-x, r, 1.0), r);
-  return r;
-}
-
 // ------------------------------------------------------------------ launch plan / shared layout
 struct CPlan {
   int ok;                     // 0: the condensed path is not available for this (dtype, n, m, e)
@@ -70,77 +57,133 @@ struct CPlan {
   int wcap;                   // capacity (elements) of W and Fd
   int smem_bytes;
   int ctas_per_sm;
+  int flags;                  // experiment switches (LCPB200_COND_FLAGS): 1 = 1/d in fp64, 2 = rz - rs/d in fp64
+  // byte offsets into the dynamic shared memory (filled by carve_plan)
+  int o_K, o_W, o_scr, o_bx, o_rdiag, o_Fd, o_Gd, o_As, o_x, o_rx, o_dx, o_qd, o_y, o_ry, o_dy,
+      o_s, o_z, o_d, o_rz, o_ds, o_dz, o_rs2, o_red, o_rows, o_posof, o_clist, o_ccols, o_ncols, o_clcnt, o_misc;
 };
 
+__host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+// structure-build scratch: Fi,Gi (u16 KS*m each), Fv,Gv (T KS*m each), 5 int arrays of m, member
+// lists (u16 CSMAX*m), column bitmaps (8 words per component), unsorted column lists (u16 LMAX*n + n ints)
+__host__ __device__ inline size_t scratch_bytes(int n, int m, int tsize) {
+  return al16((size_t)2 * KS * m * 2) + al16((size_t)2 * KS * m * tsize) + al16((size_t)5 * m * 4) +
+         al16((size_t)CSMAX * m * 2) + al16((size_t)8 * m * 4) + al16((size_t)LMAX * n * 2) + al16((size_t)n * 4) + 64;
+}
+
+// Lays the shared memory out (offsets into P) and returns the total. tsize = sizeof(T).
+inline size_t carve_plan(CPlan& P, int tsize) {
+  size_t o = 0;
+  const int n = P.n, m = P.m, e = P.e, NP = P.NP, pcap = P.pcap, wcap = P.wcap;
+#define CND_TAKE(field, bytes) do { P.field = (int)o; o += al16((size_t)(bytes)); } while (0)
+  size_t kb = (size_t)NP * NP * 8;                              // K | structure scratch | LU broadcast buffers
+  if (scratch_bytes(n, m, tsize) > kb) kb = scratch_bytes(n, m, tsize);
+  if ((size_t)8 * NP * 8 > kb) kb = (size_t)8 * NP * 8;
+  { const size_t qn = (NP + 31) / 32, sl = (size_t)(NP / qn) * qn * qn * 32 * 8; if (sl > kb) kb = sl; }   // SolveLayout
+  CND_TAKE(o_K, kb);
+  CND_TAKE(o_W, (size_t)wcap * 8);
+  CND_TAKE(o_scr, (size_t)pcap * 8);
+  CND_TAKE(o_bx, (size_t)NP * 8);
+  CND_TAKE(o_rdiag, (size_t)NP * 8);
+  CND_TAKE(o_Fd, (size_t)wcap * tsize);
+  CND_TAKE(o_Gd, (size_t)UC * pcap * tsize);
+  CND_TAKE(o_As, (size_t)e * n * tsize);
+  CND_TAKE(o_x, n * tsize); CND_TAKE(o_rx, n * tsize); CND_TAKE(o_dx, n * tsize); CND_TAKE(o_qd, n * tsize);
+  CND_TAKE(o_y, e * tsize); CND_TAKE(o_ry, e * tsize); CND_TAKE(o_dy, e * tsize);
+  CND_TAKE(o_s, m * tsize); CND_TAKE(o_z, m * tsize); CND_TAKE(o_d, m * tsize); CND_TAKE(o_rz, m * tsize);
+  CND_TAKE(o_ds, m * tsize); CND_TAKE(o_dz, m * tsize); CND_TAKE(o_rs2, m * tsize);
+  CND_TAKE(o_red, 192 * tsize);
+  CND_TAKE(o_rows, pcap * 2);
+  CND_TAKE(o_posof, m * 2);
+  CND_TAKE(o_clist, LMAX * n * 2);
+  CND_TAKE(o_ccols, UC * pcap);
+  CND_TAKE(o_ncols, pcap);
+  CND_TAKE(o_clcnt, n);
+  CND_TAKE(o_misc, 16 * 4);
+#undef CND_TAKE
+  return o;
+}
+
+extern __shared__ __align__(16) unsigned char cnd_smem[];
+
+// Accessors: every array is cnd_smem + an offset that lives in the kernel parameters (constant
+// bank), so no pointer is kept in a register across phases.
 template <typename T>
 struct CSmem {
-  double* K;                  // NP*NP (column major) | structure scratch | LU broadcast buffers
-  double* W;                  // wcap: M_c^-1, component-major, stride cs*cs
-  double* scr;                // pcap
-  double* bx;                 // NP: right-hand side / solution of the condensed system
-  double* rdiag;              // NP: 1 / u_kk
-  T *Fd, *Gd, *As;            // wcap | UC*pcap (slot-major) | e*n
-  T *x, *rx, *dx, *qd, *y, *ry, *dy;
-  T *s, *z, *d, *rz, *ds, *dz, *rs2;
-  T* red;                     // 128
-  unsigned short *rows, *posof, *clist;       // pcap | m | LMAX*n
-  unsigned char *ccols, *ncols, *clcnt;       // UC*pcap (slot-major, per component) | pcap | n
-  int* misc;                  // 16 ints
-  __host__ __device__ static size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
-  __host__ __device__ static size_t scratch_bytes(int n, int m) {
-    // structure-build scratch: Fi,Gi (u16 KS*m each), Fv,Gv (T KS*m each), 5 int arrays of m
-    return al16((size_t)2 * KS * m * 2) + al16((size_t)2 * KS * m * sizeof(T)) + al16((size_t)5 * m * 4) + 64;
-  }
-  __host__ __device__ size_t carve(char* base, const CPlan& P) {
-    size_t o = 0;
-    const int n = P.n, m = P.m, e = P.e, NP = P.NP, pcap = P.pcap, wcap = P.wcap;
-#define CND_TAKE(ptr, type, cnt) do { ptr = reinterpret_cast<type*>(base + o); o += al16((size_t)(cnt) * sizeof(type)); } while (0)
-    size_t kb = (size_t)NP * NP * 8;
-    const size_t sb = scratch_bytes(n, m);
-    const size_t lb = (size_t)8 * NP * 8;                       // LU broadcast buffers (2 x 4 x NP doubles)
-    if (sb > kb) kb = sb;
-    if (lb > kb) kb = lb;
-    K = reinterpret_cast<double*>(base + o); o += al16(kb);
-    CND_TAKE(W, double, wcap);
-    CND_TAKE(scr, double, pcap);
-    CND_TAKE(bx, double, NP);
-    CND_TAKE(rdiag, double, NP);
-    CND_TAKE(Fd, T, wcap);
-    CND_TAKE(Gd, T, UC * pcap);
-    CND_TAKE(As, T, e * n);
-    CND_TAKE(x, T, n); CND_TAKE(rx, T, n); CND_TAKE(dx, T, n); CND_TAKE(qd, T, n);
-    CND_TAKE(y, T, e); CND_TAKE(ry, T, e); CND_TAKE(dy, T, e);
-    CND_TAKE(s, T, m); CND_TAKE(z, T, m); CND_TAKE(d, T, m); CND_TAKE(rz, T, m);
-    CND_TAKE(ds, T, m); CND_TAKE(dz, T, m); CND_TAKE(rs2, T, m);
-    CND_TAKE(red, T, 128);
-    CND_TAKE(rows, unsigned short, pcap);
-    CND_TAKE(posof, unsigned short, m);
-    CND_TAKE(clist, unsigned short, LMAX * n);
-    CND_TAKE(ccols, unsigned char, UC * pcap);
-    CND_TAKE(ncols, unsigned char, pcap);
-    CND_TAKE(clcnt, unsigned char, n);
-    CND_TAKE(misc, int, 16);
-#undef CND_TAKE
-    return o;
-  }
+  const CPlan& P;
+  __device__ __forceinline__ explicit CSmem(const CPlan& p) : P(p) {}
+#define CND_ACC(name, type) __device__ __forceinline__ type* name() const { return reinterpret_cast<type*>(cnd_smem + P.o_##name); }
+  CND_ACC(K, double) CND_ACC(W, double) CND_ACC(scr, double) CND_ACC(bx, double) CND_ACC(rdiag, double)
+  CND_ACC(Fd, T) CND_ACC(Gd, T) CND_ACC(As, T)
+  CND_ACC(x, T) CND_ACC(rx, T) CND_ACC(dx, T) CND_ACC(qd, T) CND_ACC(y, T) CND_ACC(ry, T) CND_ACC(dy, T)
+  CND_ACC(s, T) CND_ACC(z, T) CND_ACC(d, T) CND_ACC(rz, T) CND_ACC(ds, T) CND_ACC(dz, T) CND_ACC(rs2, T)
+  CND_ACC(red, T)
+  CND_ACC(rows, unsigned short) CND_ACC(posof, unsigned short) CND_ACC(clist, unsigned short)
+  CND_ACC(ccols, unsigned char) CND_ACC(ncols, unsigned char) CND_ACC(clcnt, unsigned char)
+  CND_ACC(misc, int)
+#undef CND_ACC
 };
 
 // per-scene structure facts (uniform across the CTA, kept in registers)
 struct Struct {
   int ncomp, cs;              // components, rows per component (uniform stride; short ones padded)
+  int sh;                     // log2 of the smallest power of two >= ncomp: (r, c) = (t >> sh, t & mask) without divisions
 };
 
-extern __shared__ __align__(16) unsigned char cnd_smem[];
+// optional per-phase SM cycle counters (thread 0 of every CTA; lcpb200_profile)
+enum { CPH_STRUCT = 0, CPH_WINV, CPH_ASSEMBLE, CPH_LU, CPH_SOLVE_RHS, CPH_SOLVE_TRI, CPH_SOLVE_POST, CPH_RESID,
+       CPH_STEP, CPH_GRADS, CPH_COUNT };
+struct Prof {
+  long long* p;               // nullptr or this CTA's CPH_COUNT counters
+  long long t;
+  __device__ __forceinline__ void start() { if (p && threadIdx.x == 0) t = clock64(); }
+  __device__ __forceinline__ void lap(int ph) {
+    if (p && threadIdx.x == 0) {
+      const long long n = clock64();
+      atomicAdd(reinterpret_cast<unsigned long long*>(p + ph), (unsigned long long)(n - t));   // no dependent load
+      t = n;
+    }
+  }
+};
 
 // ------------------------------------------------------------------ structure detection
 // Scans one dense row-major matrix (rows x cols) into KS-slot row lists (values + column indices),
-// one warp per row, ordered (deterministic). Returns non-zero (CTA-wide) if a row has > KS entries.
+// one warp per row, RP rows (all their loads) in flight per warp; ordered, hence deterministic.
+// Returns non-zero if a row has > KS entries.
 template <typename T>
 __device__ __forceinline__ int scan_rows(const T* __restrict__ A, int rows, int cols, T* vals, unsigned short* idx,
                                          int* cnt) {
-  constexpr int CH = 8;
+  constexpr int CH = 8, RP = (sizeof(T) == 8) ? 2 : 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = NT >> 5;
   int bad = 0;
+  if (cols <= 32 * CH) {
+    for (int r0 = warp * RP; r0 < rows; r0 += nw * RP) {
+      T v[RP][CH];
+#pragma unroll
+      for (int rr = 0; rr < RP; ++rr) {
+        const T* row = A + (size_t)min(r0 + rr, rows - 1) * cols;
+#pragma unroll
+        for (int q = 0; q < CH; ++q) { const int j = q * 32 + lane; v[rr][q] = j < cols ? row[j] : T(0); }
+      }
+#pragma unroll
+      for (int rr = 0; rr < RP; ++rr) {
+        const int r = r0 + rr;
+        if (r >= rows) break;
+        int c = 0;
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+          const bool nz = v[rr][q] != T(0);
+          const unsigned mask = __ballot_sync(FULL, nz);
+          const int pos = c + __popc(mask & ((1u << lane) - 1u));
+          if (nz && pos < KS) { vals[pos * rows + r] = v[rr][q]; idx[pos * rows + r] = (unsigned short)(q * 32 + lane); }
+          c += __popc(mask);
+        }
+        if (c > KS) bad = 1;
+        if (lane == 0) cnt[r] = c;
+      }
+    }
+    return bad;
+  }
   for (int r = warp; r < rows; r += nw) {
     const T* row = A + (size_t)r * cols;
     int c = 0;
@@ -163,6 +206,12 @@ __device__ __forceinline__ int scan_rows(const T* __restrict__ A, int rows, int 
   return bad;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p, size_t bytes) {
+  const char* c = reinterpret_cast<const char*>(p);
+  for (size_t o = (size_t)threadIdx.x * 128; o < bytes; o += (size_t)NT * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + o));
+}
+
 // Builds the per-scene structure in shared memory. Returns false (uniformly) when the scene does
 // not have the structure this path needs. *singular is set when Q has a zero / non-finite diagonal
 // entry (the reference fails its LU of Q, pdipm.py:361-368).
@@ -170,37 +219,50 @@ template <typename T>
 __device__ __noinline__ bool build_structure(const CPlan& P, CSmem<T>& S, Struct& st, const T* __restrict__ Q,
                                              const T* __restrict__ G, const T* __restrict__ A,
                                              const T* __restrict__ F, int* singular) {
-  const int n = P.n, m = P.m, e = P.e, tid = threadIdx.x;
+  const int n = P.n, m = P.m, e = P.e, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pcap = P.pcap;
+  // the inputs are read exactly once, here: pull them towards L2 before the first dependent load
+  prefetch_l2(F, (size_t)m * m * sizeof(T));
+  prefetch_l2(G, (size_t)m * n * sizeof(T));
+  prefetch_l2(Q, (size_t)n * n * sizeof(T));
   // scratch carved from the K region
-  char* sb = reinterpret_cast<char*>(S.K);
+  char* sb = reinterpret_cast<char*>(S.K());
   unsigned short* Fi = reinterpret_cast<unsigned short*>(sb);
   unsigned short* Gi = Fi + (size_t)KS * m;
-  size_t o = CSmem<T>::al16((size_t)2 * KS * m * 2);
+  size_t o = al16((size_t)2 * KS * m * 2);
   T* Fv = reinterpret_cast<T*>(sb + o);
   T* Gv = Fv + (size_t)KS * m;
-  o += CSmem<T>::al16((size_t)2 * KS * m * sizeof(T));
+  o += al16((size_t)2 * KS * m * sizeof(T));
   int* Fcnt = reinterpret_cast<int*>(sb + o);
   int* Gcnt = Fcnt + m;
   int* label = Gcnt + m;
   int* cidx = label + m;       // component index of a root row
-  int* csize = cidx + m;       // rows per component (indexed by component)
-  int* flags = S.misc;         // [0] bad, [1] changed, [2] ncomp, [3] csmax, [4] singular
+  int* memcnt = cidx + m;      // rows of the component rooted at row l
+  o += al16((size_t)5 * m * 4);
+  unsigned short* memb = reinterpret_cast<unsigned short*>(sb + o);      // [m][CSMAX] member rows, unordered
+  o += al16((size_t)CSMAX * m * 2);
+  unsigned* cmap = reinterpret_cast<unsigned*>(sb + o);                  // [ncomp][8] column bitmaps
+  o += al16((size_t)8 * m * 4);
+  unsigned short* cl_tmp = reinterpret_cast<unsigned short*>(sb + o);    // [LMAX][n] unsorted column lists
+  o += al16((size_t)LMAX * n * 2);
+  int* cl_cnt = reinterpret_cast<int*>(sb + o);
+  int* flags = S.misc();       // [0..7] flags, [8..15] warp totals
 
-  if (tid < 8) flags[tid] = 0;
+  if (tid < 16) flags[tid] = 0;
   // ---- Q must be diagonal (every mass matrix world.py:57-61 builds)
   int bad = 0;
   for (int t = tid; t < n * n; t += NT) {
     const int i = t / n, j = t - i * n;
     const T q = Q[t];
     if (i == j) {
-      S.qd[i] = q;
+      S.qd()[i] = q;
       if (!(q != T(0) && isfinite((double)q))) bad |= 2;
     } else if (q != T(0)) bad |= 1;
   }
   bad |= scan_rows<T>(F, m, m, Fv, Fi, Fcnt) ? 1 : 0;
   bad |= scan_rows<T>(G, m, n, Gv, Gi, Gcnt) ? 1 : 0;
-  for (int t = tid; t < e * n; t += NT) S.As[t] = A[t];
-  for (int i = tid; i < m; i += NT) label[i] = i;
+  for (int t = tid; t < e * n; t += NT) S.As()[t] = A[t];
+  for (int i = tid; i < m; i += NT) { label[i] = i; memcnt[i] = 0; }
+  for (int a = tid; a < n; a += NT) cl_cnt[a] = 0;
   const int anybad = __syncthreads_or(bad);
   if (anybad & 2) { *singular = 1; return false; }
   if (anybad & 1) return false;
@@ -222,222 +284,254 @@ __device__ __noinline__ bool build_structure(const CPlan& P, CSmem<T>& S, Struct
     if (!__syncthreads_or(changed)) break;
     if (pass == 63) return false;
   }
-  // ---- component index = rank of the root among roots (ordered by row), slot = rank inside it
-  for (int i = tid; i < m; i += NT) csize[i] = 0;
-  __syncthreads();
-  {
-    // exclusive count of roots before row i (m is a few hundred: a direct count per thread)
-    for (int i = tid; i < m; i += NT) {
-      if (label[i] == i) {
-        int c = 0;
-        for (int j = 0; j < i; ++j) c += (label[j] == j);
-        cidx[i] = c;
-        atomicMax(&flags[2], c + 1);
-      }
-    }
-  }
-  __syncthreads();
-  const int ncomp = flags[2];
-  int myslot[4];                      // up to 4 rows per thread (m <= 1024)
+  // ---- component index = rank of the root among roots (ballot prefix sums); member lists
   if (m > 4 * NT) return false;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int i = tid + q * NT;
-    myslot[q] = 0;
+  int running = 0;
+  for (int base = 0; base < m; base += NT) {
+    const int i = base + tid;
+    const bool root = i < m && label[i] == i;
+    const unsigned mask = __ballot_sync(FULL, root);
+    if (lane == 0) flags[8 + warp] = __popc(mask);
+    __syncthreads();
+    int before = running;
+    for (int w = 0; w < warp; ++w) before += flags[8 + w];
+    int total = 0;
+    for (int w = 0; w < (NT >> 5); ++w) total += flags[8 + w];
+    if (root) cidx[i] = before + __popc(mask & ((1u << lane) - 1u));
     if (i < m) {
       const int l = label[i];
-      int r = 0;
-      for (int j = l; j < i; ++j) r += (label[j] == l);
-      myslot[q] = r;
-      atomicMax(&csize[cidx[l]], r + 1);
+      const int slot = atomicAdd(&memcnt[l], 1);
+      if (slot < CSMAX) memb[l * CSMAX + slot] = (unsigned short)i;
     }
+    running += total;
+    __syncthreads();
   }
-  __syncthreads();
+  const int ncomp = running;
   {
     int mx = 0;
-    for (int c = tid; c < ncomp; c += NT) mx = max(mx, csize[c]);
-    atomicMax(&flags[3], mx);
+    for (int i = tid; i < m; i += NT) mx = max(mx, memcnt[i]);
+    if (mx > 0) atomicMax(&flags[3], mx);
   }
   __syncthreads();
   const int cs = flags[3];
-  if (cs > CSMAX || ncomp * cs > P.pcap || ncomp * cs * cs > P.wcap || ncomp > 8191) return false;
+  if (cs > CSMAX || ncomp * cs > pcap || ncomp * cs * cs > P.wcap || ncomp > 8191) return false;
   st.ncomp = ncomp; st.cs = cs;
+  st.sh = 0;
+  while ((1 << st.sh) < ncomp) ++st.sh;
   const int npos = ncomp * cs;
-  // ---- rows <-> positions, Fd, union columns, Gd
-  for (int p = tid; p < npos; p += NT) { S.rows[p] = 0xFFFF; S.ncols[p] = 0; }
-  for (int t = tid; t < ncomp * cs * cs; t += NT) S.Fd[t] = T(0);
-  for (int t = tid; t < UC * P.pcap; t += NT) { S.Gd[t] = T(0); S.ccols[t] = 0; }
+  for (int p = tid; p < npos; p += NT) { S.rows()[p] = 0xFFFF; S.ncols()[p] = 0; }
+  for (int t = tid; t < ncomp * cs * cs; t += NT) S.Fd()[t] = T(0);
+  for (int t = tid; t < UC * pcap; t += NT) { S.Gd()[t] = T(0); S.ccols()[t] = 0; }
+  for (int t = tid; t < 8 * ncomp; t += NT) cmap[t] = 0u;
   __syncthreads();
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int i = tid + q * NT;
-    if (i < m) {
-      const int pos = cidx[label[i]] * cs + myslot[q];
-      S.rows[pos] = (unsigned short)i;
-      S.posof[i] = (unsigned short)pos;
-    }
+  // ---- rows <-> positions (slot = rank of the row inside its component), column bitmaps
+  for (int i = tid; i < m; i += NT) {
+    const int l = label[i], c = cidx[l], cnt = memcnt[l];
+    int r = 0;
+    for (int t = 0; t < cnt; ++t) r += (memb[l * CSMAX + t] < i);
+    const int pos = r * ncomp + c;
+    S.rows()[pos] = (unsigned short)i;
+    S.posof()[i] = (unsigned short)pos;
+    const int gc = Gcnt[i];
+    for (int k = 0; k < gc; ++k) { const int col = Gi[k * m + i]; atomicOr(&cmap[c * 8 + (col >> 5)], 1u << (col & 31)); }
   }
   __syncthreads();
+  // ---- Fd, Gd (slot of a column = its rank in the component's bitmap), sorted column lists
+  int bad2 = 0;
   for (int i = tid; i < m; i += NT) {
-    const int pos = S.posof[i], c = pos / cs, r = pos - c * cs;
+    const int pos = S.posof()[i], r = pos / ncomp, c = pos - r * ncomp;
     const int fc = Fcnt[i];
     for (int k = 0; k < fc; ++k) {
-      const int pj = S.posof[Fi[k * m + i]];
-      S.Fd[(size_t)c * cs * cs + r * cs + (pj - c * cs)] = Fv[k * m + i];
+      const int pj = S.posof()[Fi[k * m + i]];
+      S.Fd()[(size_t)(r * cs + pj / ncomp) * ncomp + c] = Fv[k * m + i];
+    }
+    const int gc = Gcnt[i];
+    for (int k = 0; k < gc; ++k) {
+      const int col = Gi[k * m + i], wd = col >> 5;
+      int p = __popc(cmap[c * 8 + wd] & ((1u << (col & 31)) - 1u));
+      for (int w = 0; w < wd; ++w) p += __popc(cmap[c * 8 + w]);
+      if (p < UC) { S.Gd()[(size_t)p * pcap + pos] = Gv[k * m + i]; S.ccols()[p * pcap + c] = (unsigned char)col; }
     }
   }
-  int bad2 = 0;
-  for (int c = tid; c < ncomp; c += NT) {           // sorted union of the columns of the component's rows
+  for (int c = tid; c < ncomp; c += NT) {
     int cnt = 0;
-    for (int r = 0; r < cs; ++r) {
-      const int i = S.rows[c * cs + r];
-      if (i == 0xFFFF) continue;
-      const int gc = Gcnt[i];
-      for (int k = 0; k < gc; ++k) {
-        const int col = Gi[k * m + i];
-        int p = 0;
-        while (p < cnt && S.ccols[p * P.pcap + c] < col) ++p;
-        if (p < cnt && S.ccols[p * P.pcap + c] == col) continue;
-        if (cnt == UC) { bad2 = 1; break; }
-        for (int t = cnt; t > p; --t) S.ccols[t * P.pcap + c] = S.ccols[(t - 1) * P.pcap + c];
-        S.ccols[p * P.pcap + c] = (unsigned char)col;
-        ++cnt;
-      }
-    }
-    S.ncols[c] = (unsigned char)cnt;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) cnt += __popc(cmap[c * 8 + w]);
+    if (cnt > UC) bad2 = 1;
+    S.ncols()[c] = (unsigned char)min(cnt, UC);
   }
   if (__syncthreads_or(bad2)) return false;
-  for (int i = tid; i < m; i += NT) {
-    const int pos = S.posof[i], c = pos / cs;
-    const int gc = Gcnt[i], nc = S.ncols[c];
-    for (int k = 0; k < gc; ++k) {
-      const int col = Gi[k * m + i];
-      int p = 0;
-      while (p < nc && S.ccols[p * P.pcap + c] != col) ++p;
-      S.Gd[(size_t)p * P.pcap + pos] = Gv[k * m + i];
-    }
-  }
-  // ---- per-column lists of (component, slot): G^T w and the assembly of K gather through them
+  // per-column lists of (component, slot): G^T w and the assembly of K gather through them.
+  // Filled in arrival order, then ranked (entries are distinct) so that the order is deterministic.
   int bad3 = 0;
-  for (int a = tid; a < n; a += NT) {
-    int cnt = 0;
-    for (int c = 0; c < ncomp; ++c) {
-      const int nc = S.ncols[c];
-      for (int p = 0; p < nc; ++p)
-        if (S.ccols[p * P.pcap + c] == a) {
-          if (cnt < LMAX) S.clist[cnt * n + a] = (unsigned short)(c * 8 + p);
-          ++cnt;
-        }
+  for (int t = tid; t < ncomp * UC; t += NT) {
+    const int c = t / UC, p = t - c * UC;
+    if (p < S.ncols()[c]) {
+      const int a = S.ccols()[p * pcap + c];
+      const int slot = atomicAdd(&cl_cnt[a], 1);
+      if (slot < LMAX) cl_tmp[slot * n + a] = (unsigned short)(c * 8 + p); else bad3 = 1;
     }
-    if (cnt > LMAX) bad3 = 1;
-    S.clcnt[a] = (unsigned char)min(cnt, LMAX);
   }
   if (__syncthreads_or(bad3)) return false;
+  for (int t = tid; t < n * LMAX; t += NT) {
+    const int a = t % n, l = t / n, cnt = cl_cnt[a];
+    if (l < cnt) {
+      const int v = cl_tmp[l * n + a];
+      int rank = 0;
+      for (int u = 0; u < cnt; ++u) rank += (cl_tmp[u * n + a] < v);
+      S.clist()[rank * n + a] = (unsigned short)v;
+    }
+    if (l == 0) S.clcnt()[a] = (unsigned char)cnt;
+  }
+  __syncthreads();
   return true;
 }
 
+__device__ __forceinline__ double rcp64_fast(double x) {
+  // MUFU.RCP64H seed (>= 20 bits) + 2 Newton steps; exact division outside the seed's range
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double ax = fabs(x);
+  if (!(ax > 1e-290 && ax < 1e290)) return 1.0 / x;
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+
 // ------------------------------------------------------------------ W_c = (Fd_c + diag(1/d))^-1
-// One thread per component, Gauss-Jordan with partial pivoting on [M | I] held in registers
-// (static indices only: row interchanges are conditional swaps).
+// One thread per component: in-place Gauss-Jordan with partial pivoting, the block held in
+// registers (static indices only: row interchanges are conditional swaps, recorded in a bit mask and
+// undone as column swaps in reverse order at the end). Slot-major arrays: thread c reads / writes
+// consecutive addresses (no bank conflicts).
 template <typename T, int CS>
 __device__ __forceinline__ void comp_inverse(const CPlan& P, CSmem<T>& S, const Struct& st) {
-  for (int c = threadIdx.x; c < st.ncomp; c += NT) {
-    double M[CS][CS], V[CS][CS];
+  const int nc_ = st.ncomp;                       // positions are slot-major: pos(c, r) = r * ncomp + c
+  for (int c = threadIdx.x; c < nc_; c += NT) {
+    double M[CS][CS];
 #pragma unroll
     for (int r = 0; r < CS; ++r) {
-      const int i = S.rows[c * CS + r];
+      const int i = S.rows()[r * nc_ + c];
 #pragma unroll
-      for (int q = 0; q < CS; ++q) {
-        M[r][q] = (double)S.Fd[(size_t)c * CS * CS + r * CS + q];
-        V[r][q] = (r == q) ? 1.0 : 0.0;
-      }
-      M[r][r] += (i == 0xFFFF) ? 1.0 : 1.0 / (double)S.d[i];
+      for (int q = 0; q < CS; ++q) M[r][q] = (double)S.Fd()[(size_t)(r * CS + q) * nc_ + c];
+      M[r][r] += (i == 0xFFFF) ? 1.0 : ((P.flags & 1) ? 1.0 / (double)S.d()[i] : (double)(T(1) / S.d()[i]));      // 1/d in the I/O dtype (pdipm.py:427-429)
     }
+    unsigned swaps = 0;
+    int bit = 0;
 #pragma unroll
     for (int k = 0; k < CS; ++k) {
 #pragma unroll
       for (int i = k + 1; i < CS; ++i) {           // bring the largest |M[i][k]|, i >= k, to row k
         const bool sw = fabs(M[i][k]) > fabs(M[k][k]);
+        swaps |= (sw ? 1u : 0u) << bit;
+        ++bit;
 #pragma unroll
-        for (int q = 0; q < CS; ++q) {
-          const double a = M[k][q], b = M[i][q]; M[k][q] = sw ? b : a; M[i][q] = sw ? a : b;
-          const double u = V[k][q], w = V[i][q]; V[k][q] = sw ? w : u; V[i][q] = sw ? u : w;
-        }
+        for (int q = 0; q < CS; ++q) { const double u = M[k][q], w = M[i][q]; M[k][q] = sw ? w : u; M[i][q] = sw ? u : w; }
       }
-      const double r = 1.0 / M[k][k];
+      const double r = rcp64_fast(M[k][k]);
+      M[k][k] = 1.0;
 #pragma unroll
-      for (int q = 0; q < CS; ++q) { M[k][q] *= r; V[k][q] *= r; }
+      for (int q = 0; q < CS; ++q) M[k][q] *= r;
 #pragma unroll
       for (int i = 0; i < CS; ++i) {
         if (i == k) continue;
         const double f = M[i][k];
+        M[i][k] = 0.0;
 #pragma unroll
-        for (int q = 0; q < CS; ++q) { M[i][q] = fma(-f, M[k][q], M[i][q]); V[i][q] = fma(-f, V[k][q], V[i][q]); }
+        for (int q = 0; q < CS; ++q) M[i][q] = fma(-f, M[k][q], M[i][q]);
+      }
+    }
+#pragma unroll
+    for (int k = CS - 1; k >= 0; --k) {
+#pragma unroll
+      for (int i = CS - 1; i > k; --i) {
+        --bit;
+        const bool sw = (swaps >> bit) & 1u;
+#pragma unroll
+        for (int q = 0; q < CS; ++q) { const double u = M[q][k], w = M[q][i]; M[q][k] = sw ? w : u; M[q][i] = sw ? u : w; }
       }
     }
 #pragma unroll
     for (int r = 0; r < CS; ++r)
 #pragma unroll
-      for (int q = 0; q < CS; ++q) S.W[(size_t)c * CS * CS + r * CS + q] = V[r][q];
+      for (int q = 0; q < CS; ++q) S.W()[(size_t)(r * CS + q) * nc_ + c] = M[r][q];
   }
 }
 
-// out_c = W_c * in_c for every component, in place in S.scr (one thread per component)
+// out_c = W_c * in_c for every component, in place in S.scr (one thread per (component, row))
 template <typename T, int CS>
 __device__ __forceinline__ void comp_apply(CSmem<T>& S, const Struct& st) {
-  for (int c = threadIdx.x; c < st.ncomp; c += NT) {
-    double v[CS], w[CS];
+  const int nc_ = st.ncomp;                       // positions are slot-major: pos(c, r) = r * ncomp + c
+  const int npos = nc_ * CS;
+  const int sh = st.sh, cmask = (1 << sh) - 1, tot = CS << sh;
+  double val[4];
 #pragma unroll
-    for (int r = 0; r < CS; ++r) v[r] = S.scr[c * CS + r];
+  for (int u = 0; u < 4; ++u) {
+    const int t = threadIdx.x + u * NT, r = t >> sh, c = t & cmask;
+    val[u] = 0.0;
+    if (t < tot && c < nc_) {
+      double a = 0.0;
 #pragma unroll
-    for (int r = 0; r < CS; ++r) {
-      double a = 0;
-#pragma unroll
-      for (int q = 0; q < CS; ++q) a = fma(S.W[(size_t)c * CS * CS + r * CS + q], v[q], a);
-      w[r] = a;
+      for (int q = 0; q < CS; ++q) a = fma(S.W()[(size_t)(r * CS + q) * nc_ + c], S.scr()[q * nc_ + c], a);
+      val[u] = a;
     }
-#pragma unroll
-    for (int r = 0; r < CS; ++r) S.scr[c * CS + r] = w[r];
   }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int t = threadIdx.x + u * NT, r = t >> sh, c = t & cmask;
+    if (t < tot && c < nc_) S.scr()[r * nc_ + c] = val[u];
+  }
+  (void)npos;
 }
 
 // ------------------------------------------------------------------ K (column major, fp64)
-// Kbar = [[Q + G^T W G, A^T], [A, 0]] padded with an identity block to NP. Row owner a gathers the
-// contributions of the components that touch column a (deterministic order).
-template <typename T, int CS>
+// Kbar = [[Q + G^T W G, A^T], [A, 0]] padded with an identity block to NP. A group of UC = 8 lanes
+// owns one row a of K: lane q2 of the group adds the contribution of list entry l (component c, slot
+// p of column a) to K[a][column q2 of c]; the groups walk their lists in lockstep (__syncwarp
+// between entries), so every entry of K is accumulated in list order -- deterministic, no atomics.
+template <typename T, int NS, int CS>
 __device__ __forceinline__ void assemble_K(const CPlan& P, CSmem<T>& S, const Struct& st) {
-  const int n = P.n, e = P.e, N = P.N, NP = P.NP, tid = threadIdx.x, pcap = P.pcap;
-  double* K = S.K;
-  for (int t = tid; t < NP * NP; t += NT) {
-    const int j = t / NP, i = t - j * NP;           // K[i][j] at K[j*NP + i]
-    double v = 0.0;
-    if (i < n && j < n) v = (i == j) ? (double)S.qd[i] : 0.0;
-    else if (i < n && j < N) v = (double)S.As[(j - n) * n + i];
-    else if (j < n && i < N) v = (double)S.As[(i - n) * n + j];
-    else if (i >= N && i == j) v = 1.0;
-    K[t] = v;
+  const int nc_ = st.ncomp;                       // positions are slot-major: pos(c, r) = r * ncomp + c
+  constexpr int NP = 16 * NS;
+  const int n = P.n, N = P.N, e = P.e, tid = threadIdx.x, pcap = P.pcap;
+  double* K = S.K();
+  {
+    double2* K2 = reinterpret_cast<double2*>(K);
+    for (int t = tid; t < NP * NP / 2; t += NT) K2[t] = make_double2(0.0, 0.0);
   }
   __syncthreads();
-  for (int a = tid; a < n; a += NT) {
-    const int cnt = S.clcnt[a];
-    for (int l = 0; l < cnt; ++l) {
-      const int cp = S.clist[l * n + a], c = cp >> 3, p = cp & 7;
-      double u[CS];
+  for (int i = tid; i < NP; i += NT) K[(size_t)i * NP + i] = i < n ? (double)S.qd()[i] : (i < N ? 0.0 : 1.0);
+  for (int t = tid; t < e * n; t += NT) {
+    const int k = t / n, i = t - k * n;
+    const double v = (double)S.As()[t];
+    K[(size_t)(n + k) * NP + i] = v;                 // A^T: K[i][n+k]
+    K[(size_t)i * NP + n + k] = v;                   // A  : K[n+k][i]
+  }
+  __syncthreads();
+  const int grp = tid >> 3, q2 = tid & 7;            // 32 groups of 8 lanes
+  for (int a0 = 0; a0 < n; a0 += NT / 8) {
+    const int a = a0 + grp;
+    const int cnt = a < n ? (int)S.clcnt()[a] : 0;
+    int mx = cnt;                                    // warp-uniform trip count (4 groups per warp)
+    mx = max(mx, __shfl_xor_sync(FULL, mx, 8));
+    mx = max(mx, __shfl_xor_sync(FULL, mx, 16));
+    for (int l = 0; l < mx; ++l) {
+      if (l < cnt) {
+        const int cp = S.clist()[l * n + a], c = cp >> 3, p = cp & 7;
+        if (q2 < (int)S.ncols()[c]) {
+          double acc = 0.0;
 #pragma unroll
-      for (int q = 0; q < CS; ++q) u[q] = 0.0;
+          for (int q = 0; q < CS; ++q) {             // u_q = sum_r Gd[r][p] W[r][q];  acc += u_q Gd[q][q2]
+            double u = 0.0;
 #pragma unroll
-      for (int r = 0; r < CS; ++r) {
-        const double g = (double)S.Gd[(size_t)p * pcap + c * CS + r];
-#pragma unroll
-        for (int q = 0; q < CS; ++q) u[q] = fma(g, S.W[(size_t)c * CS * CS + r * CS + q], u[q]);
+            for (int r = 0; r < CS; ++r)
+              u = fma((double)S.Gd()[(size_t)p * pcap + r * nc_ + c], S.W()[(size_t)(r * CS + q) * nc_ + c], u);
+            acc = fma(u, (double)S.Gd()[(size_t)q2 * pcap + q * nc_ + c], acc);
+          }
+          K[(size_t)S.ccols()[q2 * pcap + c] * NP + a] += acc;
+        }
       }
-      const int nc = S.ncols[c];
-      for (int q2 = 0; q2 < nc; ++q2) {
-        double acc = 0.0;
-#pragma unroll
-        for (int q = 0; q < CS; ++q) acc = fma(u[q], (double)S.Gd[(size_t)q2 * pcap + c * CS + q], acc);
-        K[(size_t)S.ccols[q2 * pcap + c] * NP + a] += acc;
-      }
+      __syncwarp();
     }
   }
   __syncthreads();
@@ -445,86 +539,116 @@ __device__ __forceinline__ void assemble_K(const CPlan& P, CSmem<T>& S, const St
 
 // ------------------------------------------------------------------ LU in registers
 // Thread (ti = tid & 15, tj = tid >> 4) owns a[r][c] = K[16r + ti][16c + tj]. One phase = the 16
-// pivots of block B0, two per barrier. Pivot rows / columns travel through `buf` (double buffered:
-// [2][4][NP]); every thread redoes the 2x2 pivot arithmetic. No pivoting: K + its border is
-// quasi-definite (Q > 0, symmetric part of W_c is what the reference's own pivot-free GPU path
-// relies on); zero pivots produce inf/nan exactly like the reference's LU would.
+// pivots of block B0, two per barrier. Pivot rows / columns travel through shared memory as
+// interleaved pairs (U2[j] = {row k, row k+1} at column j, C2[i] = {column k, column k+1} at row i,
+// double buffered); every thread redoes the 2x2 pivot arithmetic. No pivoting: K + its border is
+// quasi-definite; zero pivots produce inf/nan exactly like the reference's LU would.
+// The loop is bound by the FP64 pipe (16 lanes / SMSP): masks are applied only in the diagonal
+// block's slots, and the two column passes keep the live registers under the 128 of 2 CTAs / SM.
 template <int NS, int B0>
-__device__ __forceinline__ void lu_phase(double (&a)[NS][NS], double* buf, double* rdiag, int NP, int& step) {
-  const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
+__device__ __forceinline__ void lu_phase(double (&a)[NS][NS], int o_buf, int o_rdiag, int& step, int ti, int tj) {
+  // Entries keep the value they had when their column became the pivot column: after the last
+  // phase a[i][j] (i > j) = u_jj L[i][j] and a[i][j] (i <= j) = U[i][j]; factor_K scales by 1/u_jj.
+  // With that convention a step is ONE masked rank-2 update, a -= m0 (x) w0 + m1 (x) w1, with
+  //   m0_i = [i > k] a_ik / a_kk,             w0_j = [j > k] a_kj,
+  //   m1_i = [i > k+1] (a_i,k+1 - m0_i a_k,k+1) / a'_k+1,k+1,   w1_j = [j > k+1] (a_k+1,j - l10 a_kj),
+  // and the masks only matter inside the diagonal block (r == B0 / c == B0).
+  constexpr int NP = 16 * NS;
+  constexpr int L = NS - B0;                          // live block rows / columns
+  constexpr int CW = (L <= 4) ? L : 3;                // columns per pass (bounds the live registers)
+  double* const rdiag = reinterpret_cast<double*>(cnd_smem + o_rdiag);
 #pragma unroll 1
   for (int kk = 0; kk < 16; kk += 2) {
     const int k = 16 * B0 + kk;
-    double* u0 = buf + (size_t)(step & 1) * 4 * NP;
-    double* u1 = u0 + NP;
-    double* c0 = u1 + NP;
-    double* c1 = c0 + NP;
+    double2* const U2 = reinterpret_cast<double2*>(cnd_smem + o_buf) + (size_t)(step & 1) * 2 * NP;
+    double2* const C2 = U2 + NP;
     ++step;
-    if (ti == kk) {
+    {
+      const int sr = ti - kk, sc = tj - kk;
+      if ((unsigned)sr < 2u) {                        // I hold part of pivot row k (sr = 0) or k+1 (sr = 1)
+        double* dst = reinterpret_cast<double*>(U2) + sr;
 #pragma unroll
-      for (int c = B0; c < NS; ++c) u0[16 * c + tj] = a[B0][c];
-    }
-    if (ti == kk + 1) {
+        for (int c = B0; c < NS; ++c) dst[2 * (16 * c + tj)] = a[B0][c];
+      }
+      if ((unsigned)sc < 2u) {                        // ... of pivot column k / k+1
+        double* dst = reinterpret_cast<double*>(C2) + sc;
 #pragma unroll
-      for (int c = B0; c < NS; ++c) u1[16 * c + tj] = a[B0][c];
-    }
-    if (tj == kk) {
-#pragma unroll
-      for (int r = B0; r < NS; ++r) c0[16 * r + ti] = a[r][B0];
-    }
-    if (tj == kk + 1) {
-#pragma unroll
-      for (int r = B0; r < NS; ++r) c1[16 * r + ti] = a[r][B0];
+        for (int r = B0; r < NS; ++r) dst[2 * (16 * r + ti)] = a[r][B0];
+      }
     }
     __syncthreads();
-    const double p00 = u0[k], p01 = u0[k + 1], p10 = u1[k], p11 = u1[k + 1];
-    const double r0 = rcp64(p00);
-    const double l10 = p10 * r0;
-    const double r1 = rcp64(fma(-l10, p01, p11));
-    if (threadIdx.x == 0) { rdiag[k] = r0; rdiag[k + 1] = r1; }
-    double w0[NS], w1[NS];                          // pivot rows restricted to my columns
+    const double2 pk = U2[k], pk1 = U2[k + 1];        // pk = {a_kk, a_k+1,k}, pk1 = {a_k,k+1, a_k+1,k+1}
+    // 1/a_kk and 1/a'_k+1,k+1 = a_kk / det(2x2 pivot block): two independent reciprocals
+    const double p01 = pk1.x;
+    const double r0 = rcp64_fast(pk.x);
+    const double r1 = pk.x * rcp64_fast(fma(pk.x, pk1.y, -(pk.y * p01)));
+    const double l10 = pk.y * r0;
+    if ((ti | tj) == 0) { rdiag[k] = r0; rdiag[k + 1] = r1; }
 #pragma unroll
-    for (int c = B0; c < NS; ++c) {
-      const int j = 16 * c + tj;
-      const double x0 = u0[j];
-      const double x1 = fma(-l10, x0, u1[j]);
-      if (ti == kk + 1 && j > k) a[B0][c] = x1;     // row k+1 of U (its entry in column k is L, below)
-      const bool live = (c > B0) || (tj > kk + 1);
-      w0[c] = live ? x0 : 0.0;
-      w1[c] = live ? x1 : 0.0;
-    }
+    for (int cg = B0; cg < NS; cg += CW) {
+      double w0[CW], w1[CW];                          // pivot rows restricted to this pass's columns
 #pragma unroll
-    for (int r = B0; r < NS; ++r) {
-      const int i = 16 * r + ti;
-      const double l0 = c0[i] * r0;
-      const double l1 = fma(-l0, p01, c1[i]) * r1;
-      const bool live = (r > B0) || (ti > kk + 1);
-      if (tj == kk && i > k) a[r][B0] = l0;
-      if (tj == kk + 1 && live) a[r][B0] = l1;
-      const double m0 = live ? l0 : 0.0, m1 = live ? l1 : 0.0;
+      for (int q = 0; q < CW; ++q) {
+        const int c = cg + q;
+        if (c < NS) {
+          const double2 u = U2[16 * c + tj];
+          const double x1 = fma(-l10, u.x, u.y);
+          w0[q] = (c == B0 && !(tj > kk)) ? 0.0 : u.x;
+          w1[q] = (c == B0 && !(tj > kk + 1)) ? 0.0 : x1;
+        }
+      }
 #pragma unroll
-      for (int c = B0; c < NS; ++c) a[r][c] = fma(-m1, w1[c], fma(-m0, w0[c], a[r][c]));
+      for (int r = B0; r < NS; ++r) {
+        const double2 cc = C2[16 * r + ti];
+        double m0 = cc.x * r0;
+        double m1 = fma(-m0, p01, cc.y) * r1;
+        if (r == B0) {
+          m0 = (ti > kk) ? m0 : 0.0;
+          m1 = (ti > kk + 1) ? m1 : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < CW; ++q) {
+          const int c = cg + q;
+          if (c < NS) a[r][c] = fma(-m1, w1[q], fma(-m0, w0[q], a[r][c]));
+        }
+      }
     }
   }
 }
 
 template <int NS, int B0>
 struct LuPhases {
-  static __device__ __forceinline__ void run(double (&a)[NS][NS], double* buf, double* rdiag, int NP, int& step) {
-    lu_phase<NS, B0>(a, buf, rdiag, NP, step);
-    LuPhases<NS, B0 + 1>::run(a, buf, rdiag, NP, step);
+  static __device__ __forceinline__ void run(double (&a)[NS][NS], int o_buf, int o_rdiag, int& step, int ti, int tj) {
+    lu_phase<NS, B0>(a, o_buf, o_rdiag, step, ti, tj);
+    LuPhases<NS, B0 + 1>::run(a, o_buf, o_rdiag, step, ti, tj);
   }
 };
 template <int NS>
 struct LuPhases<NS, NS> {
-  static __device__ __forceinline__ void run(double (&)[NS][NS], double*, double*, int, int&) {}
+  static __device__ __forceinline__ void run(double (&)[NS][NS], int, int, int&, int, int) {}
 };
 
-// K (shared, column major) -> registers -> LU -> factors back to K, transposed layout kept:
-// S[j*NP + i] = L[i][j] (i > j), U[i][j] / u_jj (i < j); rdiag[j] = 1/u_jj.
+// Layout of the factors for the substitution warp (solve_warp): lane l owns rows QN*l + q', round
+// r eliminates the QN pivots QN*r + q; entry (i, j) sits at
+//     ((r_j * QN + q'_i) * QN + q_j) * 32 + lane_i
+// so that each (q', q) pair of a round is one conflict-free 8-byte load per lane. L[i][j] for
+// i > j, U[i][j] / u_jj for i < j (the diagonal slots are unused); both are a[i][j] / u_jj.
+template <int NS> struct SolveLayout {
+  static constexpr int NP = 16 * NS;
+  static constexpr int QN = (NP + 31) / 32;
+  static constexpr int ROUNDS = NP / QN;
+  static constexpr size_t BYTES = (size_t)ROUNDS * QN * QN * 32 * 8;
+};
+
+// K (shared, column major) -> registers -> LU -> factors back to the K region in the solve layout.
 template <int NS>
-__device__ __noinline__ void factor_K(double* K, double* rdiag, int NP) {
-  const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
+__device__ __noinline__ void factor_K(int o_K, int o_rdiag) {
+  constexpr int NP = 16 * NS, QN = SolveLayout<NS>::QN;
+  int tid_;                                          // read %tid.x once (opaque to the compiler: no re-reads in the loops)
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_));
+  const int ti = tid_ & 15, tj = tid_ >> 4;
+  double* const K = reinterpret_cast<double*>(cnd_smem + o_K);
+  double* const rdiag = reinterpret_cast<double*>(cnd_smem + o_rdiag);
   double a[NS][NS];
 #pragma unroll
   for (int c = 0; c < NS; ++c)
@@ -532,107 +656,136 @@ __device__ __noinline__ void factor_K(double* K, double* rdiag, int NP) {
     for (int r = 0; r < NS; ++r) a[r][c] = K[(size_t)(16 * c + tj) * NP + 16 * r + ti];
   __syncthreads();                                   // K region becomes the broadcast buffer
   int step = 0;
-  LuPhases<NS, 0>::run(a, K, rdiag, NP, step);
+  LuPhases<NS, 0>::run(a, o_K, o_rdiag, step, ti, tj);
   __syncthreads();                                   // rdiag complete, broadcast buffers dead
+  int rowpart[NS];
+#pragma unroll
+  for (int r = 0; r < NS; ++r) { const int i = 16 * r + ti; rowpart[r] = (i % QN) * QN * 32 + i / QN; }
 #pragma unroll
   for (int c = 0; c < NS; ++c) {
     const int j = 16 * c + tj;
     const double rj = rdiag[j];
+    const int colpart = (j / QN) * QN * QN * 32 + (j % QN) * 32;
 #pragma unroll
     for (int r = 0; r < NS; ++r) {
       const int i = 16 * r + ti;
-      K[(size_t)j * NP + i] = (i < j) ? a[r][c] * rj : a[r][c];
+      K[colpart + rowpart[r]] = (i != j) ? a[r][c] * rj : a[r][c];
     }
   }
   __syncthreads();
 }
 
 // ------------------------------------------------------------------ triangular solves (ONE warp)
-// bx <- Kbar^-1 bx with the factors left by factor_K. Lane owns rows lane + 32q. Exact
-// substitution order; 4 pivots per round: their values are broadcast by shuffles, the 4x4
-// diagonal piece is solved redundantly by every lane, then each lane updates its rows.
+// bx <- Kbar^-1 bx. Exact substitution order; the QN pivots of a round belong to ONE lane (rows
+// QN*r .. QN*r + QN-1 of lane r), are broadcast by shuffles, their QN x QN triangular piece is
+// solved redundantly by every lane, then each lane updates its own rows. The coefficients of
+// round r+1 are loaded while round r's dependent chain runs (software pipeline, two register
+// sets), and the row update is predicated, not branched: the chain per round is one 64-bit shuffle
+// (26 cycles) + QN dependent DFMAs (8 cycles each).
 template <int QN>
-__device__ __noinline__ void solve_warp(const double* __restrict__ S, const double* __restrict__ rdiag,
-                                           double* bx, int NP) {
+struct SolveCoef {
+  double dg[QN * QN];         // lane r's slots (the pivots' own triangular piece), broadcast
+  double rw[QN * QN];         // this lane's slots
+};
+
+template <int QN>
+__device__ __forceinline__ void solve_load(SolveCoef<QN>& c, const double* blk, int r, int lane) {
+#pragma unroll
+  for (int t = 0; t < QN * QN; ++t) { c.dg[t] = blk[t * 32 + r]; c.rw[t] = blk[t * 32 + lane]; }
+}
+
+template <int QN>
+__device__ __forceinline__ void solve_round_fwd(double (&y)[QN], const SolveCoef<QN>& c, int r, int lane) {
+  double v[QN];
+#pragma unroll
+  for (int q = 0; q < QN; ++q) v[q] = __shfl_sync(FULL, y[q], r);
+#pragma unroll
+  for (int q = 0; q < QN; ++q)
+#pragma unroll
+    for (int qp = q + 1; qp < QN; ++qp) v[qp] = fma(-c.dg[qp * QN + q], v[q], v[qp]);
+  const bool below = lane > r, own = lane == r;
+#pragma unroll
+  for (int qp = 0; qp < QN; ++qp) {
+    double t = y[qp];
+#pragma unroll
+    for (int q = 0; q < QN; ++q) t = fma(-c.rw[qp * QN + q], v[q], t);
+    y[qp] = below ? t : (own ? v[qp] : y[qp]);
+  }
+}
+
+template <int QN>
+__device__ __forceinline__ void solve_round_bwd(double (&y)[QN], const SolveCoef<QN>& c, int r, int lane) {
+  double v[QN];
+#pragma unroll
+  for (int q = 0; q < QN; ++q) v[q] = __shfl_sync(FULL, y[q], r);
+#pragma unroll
+  for (int q = QN - 1; q >= 0; --q)
+#pragma unroll
+    for (int qp = q - 1; qp >= 0; --qp) v[qp] = fma(-c.dg[qp * QN + q], v[q], v[qp]);
+  const bool above = lane < r, own = lane == r;
+#pragma unroll
+  for (int qp = 0; qp < QN; ++qp) {
+    double t = y[qp];
+#pragma unroll
+    for (int q = QN - 1; q >= 0; --q) t = fma(-c.rw[qp * QN + q], v[q], t);
+    y[qp] = above ? t : (own ? v[qp] : y[qp]);
+  }
+}
+
+template <int NS>
+__device__ __noinline__ void solve_warp(int o_K, int o_rdiag, int o_bx) {
+  constexpr int NP = 16 * NS, QN = SolveLayout<NS>::QN, ROUNDS = SolveLayout<NS>::ROUNDS;
+  constexpr int STRIDE = QN * QN * 32;
+  static_assert(ROUNDS % 2 == 0, "the software pipeline handles two rounds per trip");
   const int lane = threadIdx.x & 31;
+  const double* const S = reinterpret_cast<const double*>(cnd_smem + o_K);
+  const double* const rdiag = reinterpret_cast<const double*>(cnd_smem + o_rdiag);
+  double* const bx = reinterpret_cast<double*>(cnd_smem + o_bx);
   double y[QN];
 #pragma unroll
-  for (int q = 0; q < QN; ++q) y[q] = (lane + 32 * q < NP) ? bx[lane + 32 * q] : 0.0;
+  for (int q = 0; q < QN; ++q) y[q] = (QN * lane + q < NP) ? bx[QN * lane + q] : 0.0;
+  SolveCoef<QN> c0, c1;
   // ---- forward: L y = b (unit lower)
-#pragma unroll
-  for (int q0 = 0; q0 < QN; ++q0) {
+  solve_load<QN>(c0, S, 0, lane);
 #pragma unroll 1
-    for (int kk = 0; kk < 8; ++kk) {
-      const int k = 32 * q0 + 4 * kk;
-      if (k >= NP) break;
-      const double* c0 = S + (size_t)k * NP;
-      const double* c1 = c0 + NP;
-      const double* c2 = c1 + NP;
-      const double* c3 = c2 + NP;
-      const double v0 = __shfl_sync(FULL, y[q0], 4 * kk), v1 = __shfl_sync(FULL, y[q0], 4 * kk + 1);
-      const double v2 = __shfl_sync(FULL, y[q0], 4 * kk + 2), v3 = __shfl_sync(FULL, y[q0], 4 * kk + 3);
-      const double y1 = fma(-c0[k + 1], v0, v1);
-      const double y2 = fma(-c1[k + 2], y1, fma(-c0[k + 2], v0, v2));
-      const double y3 = fma(-c2[k + 3], y2, fma(-c1[k + 3], y1, fma(-c0[k + 3], v0, v3)));
-#pragma unroll
-      for (int q = q0; q < QN; ++q) {
-        const int i = lane + 32 * q;
-        if (i > k + 3 && i < NP)
-          y[q] = fma(-c3[i], y3, fma(-c2[i], y2, fma(-c1[i], y1, fma(-c0[i], v0, y[q]))));
-      }
-      const int w = lane - 4 * kk;
-      if (w == 1) y[q0] = y1;
-      if (w == 2) y[q0] = y2;
-      if (w == 3) y[q0] = y3;
-    }
+  for (int r = 0; r < ROUNDS; r += 2) {
+    solve_load<QN>(c1, S + (size_t)(r + 1) * STRIDE, r + 1, lane);
+    solve_round_fwd<QN>(y, c0, r, lane);
+    const int rn = (r + 2 < ROUNDS) ? r + 2 : ROUNDS - 1;       // last trip: a harmless reload
+    solve_load<QN>(c0, S + (size_t)rn * STRIDE, rn, lane);
+    solve_round_fwd<QN>(y, c1, r + 1, lane);
   }
-  // ---- backward: U x = y with columns of U pre-scaled by 1/u_kk (z_k = u_kk x_k)
-#pragma unroll
-  for (int q0 = QN - 1; q0 >= 0; --q0) {
+  // ---- backward: U x = y with the columns of U pre-scaled by 1/u_kk (z_k = u_kk x_k)
+  // (c0 holds round ROUNDS-1 from the last trip above)
 #pragma unroll 1
-    for (int kk = 7; kk >= 0; --kk) {
-      const int k = 32 * q0 + 4 * kk;
-      if (k >= NP) continue;
-      const double* c0 = S + (size_t)k * NP;
-      const double* c1 = c0 + NP;
-      const double* c2 = c1 + NP;
-      const double* c3 = c2 + NP;
-      const double v0 = __shfl_sync(FULL, y[q0], 4 * kk), v1 = __shfl_sync(FULL, y[q0], 4 * kk + 1);
-      const double v2 = __shfl_sync(FULL, y[q0], 4 * kk + 2), v3 = __shfl_sync(FULL, y[q0], 4 * kk + 3);
-      const double z2 = fma(-c3[k + 2], v3, v2);
-      const double z1 = fma(-c2[k + 1], z2, fma(-c3[k + 1], v3, v1));
-      const double z0 = fma(-c1[k], z1, fma(-c2[k], z2, fma(-c3[k], v3, v0)));
-#pragma unroll
-      for (int q = 0; q <= q0; ++q) {
-        const int i = lane + 32 * q;
-        if (i < k) y[q] = fma(-c0[i], z0, fma(-c1[i], z1, fma(-c2[i], z2, fma(-c3[i], v3, y[q]))));
-      }
-      const int w = lane - 4 * kk;
-      if (w == 0) y[q0] = z0;
-      if (w == 1) y[q0] = z1;
-      if (w == 2) y[q0] = z2;
-    }
+  for (int r = ROUNDS - 1; r > 0; r -= 2) {
+    solve_load<QN>(c1, S + (size_t)(r - 1) * STRIDE, r - 1, lane);
+    solve_round_bwd<QN>(y, c0, r, lane);
+    const int rn = (r - 2 >= 0) ? r - 2 : 0;
+    solve_load<QN>(c0, S + (size_t)rn * STRIDE, rn, lane);
+    solve_round_bwd<QN>(y, c1, r - 1, lane);
   }
 #pragma unroll
   for (int q = 0; q < QN; ++q) {
-    const int i = lane + 32 * q;
+    const int i = QN * lane + q;
     if (i < NP) bx[i] = y[q] * rdiag[i];
   }
 }
 
 // ------------------------------------------------------------------ solve_kkt (pdipm.py:325-354)
 // Inputs (nullptr == zero vector): rx[n], rs[m], rz[m], ry[e]; outputs dx[n], ds[m], dz[m], dy[e].
-template <typename T, int CS, int QN>
-__device__ __forceinline__ void solve_kkt(const CPlan& P, CSmem<T>& S, const Struct& st, const T* rx, const T* rs,
-                                          const T* rz, const T* ry, T* dx, T* ds, T* dz, T* dy) {
+template <typename T, int CS, int NS>
+__device__ __forceinline__ void solve_kkt(const CPlan& P, CSmem<T>& S, const Struct& st, Prof& pf, const T* rx,
+                                          const T* rs, const T* rz, const T* ry, T* dx, T* ds, T* dz, T* dy) {
+  const int nc_ = st.ncomp;                       // positions are slot-major: pos(c, r) = r * ncomp + c
   const int n = P.n, e = P.e, N = P.N, NP = P.NP, tid = threadIdx.x, pcap = P.pcap;
   const int npos = st.ncomp * CS;
   // t = rz - rs/d  -> v = W t
   for (int p = tid; p < npos; p += NT) {
-    const int i = S.rows[p];
+    const int i = S.rows()[p];
     double t = 0.0;
-    if (i != 0xFFFF) t = (double)((rz ? rz[i] : T(0)) - rs[i] / S.d[i]);
-    S.scr[p] = t;
+    if (i != 0xFFFF) t = (P.flags & 2) ? ((double)(rz ? rz[i] : T(0)) - (double)rs[i] / (double)S.d()[i]) : (double)((rz ? rz[i] : T(0)) - rs[i] / S.d()[i]);
+    S.scr()[p] = t;
   }
   __syncthreads();
   comp_apply<T, CS>(S, st);
@@ -640,80 +793,91 @@ __device__ __forceinline__ void solve_kkt(const CPlan& P, CSmem<T>& S, const Str
   for (int a = tid; a < NP; a += NT) {
     double acc = 0.0;
     if (a < n) {
-      const int cnt = S.clcnt[a];
+      const int cnt = S.clcnt()[a];
       for (int l = 0; l < cnt; ++l) {
-        const int cp = S.clist[l * n + a], c = cp >> 3, p = cp & 7;
+        const int cp = S.clist()[l * n + a], c = cp >> 3, p = cp & 7;
 #pragma unroll
-        for (int r = 0; r < CS; ++r) acc = fma((double)S.Gd[(size_t)p * pcap + c * CS + r], S.scr[c * CS + r], acc);
+        for (int r = 0; r < CS; ++r) acc = fma((double)S.Gd()[(size_t)p * pcap + r * nc_ + c], S.scr()[r * nc_ + c], acc);
       }
       acc = -(double)(rx ? rx[a] : T(0)) - acc;
     } else if (a < N) {
       acc = -(double)(ry ? ry[a - n] : T(0));
     }
-    S.bx[a] = acc;
+    S.bx()[a] = acc;
   }
   __syncthreads();
-  if (tid < 32) solve_warp<QN>(S.K, S.rdiag, S.bx, NP);
+  pf.lap(CPH_SOLVE_RHS);
+  if (tid < 32) solve_warp<NS>(P.o_K, P.o_rdiag, P.o_bx);
   __syncthreads();
+  pf.lap(CPH_SOLVE_TRI);
   // dz = W (G dx + t)
-  for (int p = tid; p < npos; p += NT) {
-    const int i = S.rows[p];
+  for (int tt = tid; tt < (CS << st.sh); tt += NT) {
+    const int c = tt & ((1 << st.sh) - 1);
+    if (c >= nc_) continue;
+    const int p = (tt >> st.sh) * nc_ + c;
+    const int i = S.rows()[p];
     double t = 0.0;
     if (i != 0xFFFF) {
-      const int c = p / CS, nc = S.ncols[c];
-      t = (double)((rz ? rz[i] : T(0)) - rs[i] / S.d[i]);
-      for (int q = 0; q < nc; ++q) t = fma((double)S.Gd[(size_t)q * pcap + p], S.bx[S.ccols[q * pcap + c]], t);
+      const int nc = S.ncols()[c];
+      t = (P.flags & 2) ? ((double)(rz ? rz[i] : T(0)) - (double)rs[i] / (double)S.d()[i]) : (double)((rz ? rz[i] : T(0)) - rs[i] / S.d()[i]);
+      for (int q = 0; q < nc; ++q) t = fma((double)S.Gd()[(size_t)q * pcap + p], S.bx()[S.ccols()[q * pcap + c]], t);
     }
-    S.scr[p] = t;
+    S.scr()[p] = t;
   }
   __syncthreads();
   comp_apply<T, CS>(S, st);
   __syncthreads();
   for (int p = tid; p < npos; p += NT) {
-    const int i = S.rows[p];
+    const int i = S.rows()[p];
     if (i == 0xFFFF) continue;
-    const T wz = (T)S.scr[p];
+    const T wz = (T)S.scr()[p];
     const T rsi = rs[i];                                         // (dz may alias rs)
     dz[i] = wz;                                                  // :351
-    ds[i] = (-rsi - wz) / S.d[i];                                // :347,350
+    ds[i] = (-rsi - wz) / S.d()[i];                                // :347,350
   }
-  for (int a = tid; a < n; a += NT) dx[a] = (T)S.bx[a];
-  for (int k = tid; k < e; k += NT) dy[k] = (T)S.bx[n + k];
+  for (int a = tid; a < n; a += NT) dx[a] = (T)S.bx()[a];
+  for (int k = tid; k < e; k += NT) dy[k] = (T)S.bx()[n + k];
   __syncthreads();
+  pf.lap(CPH_SOLVE_POST);
 }
 
-// d is in S.d: W, K, LU
+// d is in S.d(): W, K, LU
 template <typename T, int NS, int CS>
-__device__ __forceinline__ void factor_kkt(const CPlan& P, CSmem<T>& S, const Struct& st) {
+__device__ __forceinline__ void factor_kkt(const CPlan& P, CSmem<T>& S, const Struct& st, Prof& pf) {
   comp_inverse<T, CS>(P, S, st);
   __syncthreads();
-  assemble_K<T, CS>(P, S, st);
-  factor_K<NS>(S.K, S.rdiag, P.NP);
+  pf.lap(CPH_WINV);
+  assemble_K<T, NS, CS>(P, S, st);
+  pf.lap(CPH_ASSEMBLE);
+  factor_K<NS>(P.o_K, P.o_rdiag);
+  pf.lap(CPH_LU);
 }
 
 // ------------------------------------------------------------------ get_step (pdipm.py:182-186), per scene
+// a = -v/dv; entries with dv > 0 are replaced by max(1, max(a)) (the maximum over ALL entries),
+// then the row minimum. One fused block reduction: max(a), min over the entries that are not
+// replaced, and whether any entry is replaced; torch NaN semantics (NaN wins min/max; python's
+// max(1.0, nan) is 1.0).
 template <typename T>
 __device__ __forceinline__ void get_steps(const T* z, const T* dz, const T* s, const T* ds, int m, T* red, T& step_z,
                                           T& step_s) {
   const T NEG_INF = -INFINITY, POS_INF = INFINITY;
   T mx[2] = {NEG_INF, NEG_INF};
-  for (int i = threadIdx.x; i < m; i += NT) {
-    mx[0] = nan_max(mx[0], -z[i] / dz[i]);
-    mx[1] = nan_max(mx[1], -s[i] / ds[i]);
-  }
-  block_reduce<T, 2>(mx, OpMax(), NEG_INF, red);
-  const T fz = (mx[0] > T(1)) ? mx[0] : T(1);                   // python max(1.0, a.max()): NaN -> 1.0
-  const T fs = (mx[1] > T(1)) ? mx[1] : T(1);
   T mn[2] = {POS_INF, POS_INF};
+  T any[2] = {T(0), T(0)};
   for (int i = threadIdx.x; i < m; i += NT) {
-    const T az = (dz[i] > T(0)) ? fz : (-z[i] / dz[i]);
-    const T as = (ds[i] > T(0)) ? fs : (-s[i] / ds[i]);
-    mn[0] = nan_min(mn[0], az);
-    mn[1] = nan_min(mn[1], as);
+    const T az = -z[i] / dz[i], as = -s[i] / ds[i];
+    mx[0] = nan_max(mx[0], az);
+    mx[1] = nan_max(mx[1], as);
+    if (dz[i] > T(0)) any[0] = T(1); else mn[0] = nan_min(mn[0], az);
+    if (ds[i] > T(0)) any[1] = T(1); else mn[1] = nan_min(mn[1], as);
   }
-  block_reduce<T, 2>(mn, OpMin(), POS_INF, red);
-  step_z = mn[0];
-  step_s = mn[1];
+  T v[6] = {mx[0], mx[1], -mn[0], -mn[1], any[0], any[1]};     // min(x) = -max(-x): one reduction operator
+  block_reduce<T, 6>(v, OpMax(), NEG_INF, red);
+  const T fz = (v[0] > T(1)) ? v[0] : T(1);                     // python max(1.0, a.max()): NaN -> 1.0
+  const T fs = (v[1] > T(1)) ? v[1] : T(1);
+  step_z = (v[4] > T(0)) ? nan_min(-v[2], fz) : -v[2];
+  step_s = (v[5] > T(0)) ? nan_min(-v[3], fs) : -v[3];
 }
 
 template <typename T>
@@ -725,6 +889,7 @@ struct CFwdArgs {
   int *status, *iters;
   T eps;
   int not_improved_lim, max_iter;
+  long long* prof;            // nullptr or [grid][CPH_COUNT]
 };
 
 template <typename T>
@@ -734,13 +899,15 @@ struct CBwdArgs {
   const T *Q, *G, *A, *F;
   const T *zhat, *nu, *lam, *slack, *g;
   T *dQ, *dp, *dG, *dh, *dA, *db, *dF;
-  int* done;                  // [B]: 1 = gradients written here, 0 = scene left to the dual-form kernel
+  int* done;                  // nullptr or [B]: 1 = gradients written here, 0 = scene left to the dual-form kernel
+  const int* only;            // nullptr or [B]: process only the scenes flagged non-zero (rescue pass after the dual form)
+  long long* prof;
 };
 
 // ------------------------------------------------------------------ forward (pdipm.py:49-179), one scene
 template <typename T, int NS, int CS>
-__device__ __forceinline__ void forward_scene(const CFwdArgs<T>& a, CSmem<T>& S, const Struct& st, int sc) {
-  constexpr int QN = (NS + 1) / 2;
+__device__ __forceinline__ void forward_scene(const CFwdArgs<T>& a, CSmem<T>& S, const Struct& st, Prof& pf, int sc) {
+  const int nc_ = st.ncomp;                       // positions are slot-major: pos(c, r) = r * ncomp + c
   const CPlan& P = a.P;
   const int n = P.n, m = P.m, e = P.e, tid = threadIdx.x, pcap = P.pcap;
   const T* p = a.p + (size_t)sc * n;
@@ -753,19 +920,19 @@ __device__ __forceinline__ void forward_scene(const CFwdArgs<T>& a, CSmem<T>& S,
   const T NANV = nan("");
 
   // ---- initial point: d = 1, rhs (p, 0, -h, -b)                 :58-63
-  for (int i = tid; i < m; i += NT) { S.d[i] = T(1); S.rs2[i] = T(0); S.rz[i] = -h[i]; }
-  for (int i = tid; i < n; i += NT) S.rx[i] = p[i];
-  for (int i = tid; i < e; i += NT) S.ry[i] = -b[i];
+  for (int i = tid; i < m; i += NT) { S.d()[i] = T(1); S.rs2()[i] = T(0); S.rz()[i] = -h[i]; }
+  for (int i = tid; i < n; i += NT) S.rx()[i] = p[i];
+  for (int i = tid; i < e; i += NT) S.ry()[i] = -b[i];
   __syncthreads();
-  factor_kkt<T, NS, CS>(P, S, st);
-  solve_kkt<T, CS, QN>(P, S, st, S.rx, S.rs2, S.rz, e > 0 ? S.ry : nullptr, S.x, S.s, S.z, S.y);
+  factor_kkt<T, NS, CS>(P, S, st, pf);
+  solve_kkt<T, CS, NS>(P, S, st, pf, S.rx(), S.rs2(), S.rz(), e > 0 ? S.ry() : nullptr, S.x(), S.s(), S.z(), S.y());
   {   // shift s and z to >= 1 where the row minimum is <= 0       :65-75
     T mn[2] = {INFINITY, INFINITY};
-    for (int i = tid; i < m; i += NT) { mn[0] = nan_min(mn[0], S.s[i]); mn[1] = nan_min(mn[1], S.z[i]); }
-    block_reduce<T, 2>(mn, OpMin(), (T)INFINITY, S.red);
+    for (int i = tid; i < m; i += NT) { mn[0] = nan_min(mn[0], S.s()[i]); mn[1] = nan_min(mn[1], S.z()[i]); }
+    block_reduce<T, 2>(mn, OpMin(), (T)INFINITY, S.red());
     for (int i = tid; i < m; i += NT) {
-      if (mn[0] <= T(0)) S.s[i] -= mn[0] - T(1);
-      if (mn[1] <= T(0)) S.z[i] -= mn[1] - T(1);
+      if (mn[0] <= T(0)) S.s()[i] -= mn[0] - T(1);
+      if (mn[1] <= T(0)) S.z()[i] -= mn[1] - T(1);
     }
     __syncthreads();
   }
@@ -778,43 +945,47 @@ __device__ __forceinline__ void forward_scene(const CFwdArgs<T>& a, CSmem<T>& S,
     // ---- residuals                                              :82-96
     for (int c = tid; c < n; c += NT) {                            // rx = G^T z + Q x + p (+ A^T y)
       T acc = 0;
-      const int cnt = S.clcnt[c];
+      const int cnt = S.clcnt()[c];
       for (int l = 0; l < cnt; ++l) {
-        const int cp = S.clist[l * n + c], cc = cp >> 3, pp = cp & 7;
+        const int cp = S.clist()[l * n + c], cc = cp >> 3, pp = cp & 7;
 #pragma unroll
         for (int r = 0; r < CS; ++r) {
-          const int i = S.rows[cc * CS + r];
-          if (i != 0xFFFF) acc = fma(S.Gd[(size_t)pp * pcap + cc * CS + r], S.z[i], acc);
+          const int i = S.rows()[r * nc_ + cc];
+          if (i != 0xFFFF) acc = fma(S.Gd()[(size_t)pp * pcap + r * nc_ + cc], S.z()[i], acc);
         }
       }
-      for (int k = 0; k < e; ++k) acc = fma(S.As[k * n + c], S.y[k], acc);
-      S.rx[c] = acc + S.qd[c] * S.x[c] + p[c];
+      for (int k = 0; k < e; ++k) acc = fma(S.As()[k * n + c], S.y()[k], acc);
+      S.rx()[c] = acc + S.qd()[c] * S.x()[c] + p[c];
     }
-    for (int pz = tid; pz < npos; pz += NT) {                       // rz = G x + s - h - F z
-      const int i = S.rows[pz];
+    for (int tt = tid; tt < (CS << st.sh); tt += NT) {              // rz = G x + s - h - F z
+      const int r = tt >> st.sh, c = tt & ((1 << st.sh) - 1);
+      if (c >= nc_) continue;
+      const int pz = r * nc_ + c;
+      const int i = S.rows()[pz];
       if (i == 0xFFFF) continue;
-      const int c = pz / CS, r = pz - c * CS, nc = S.ncols[c];
+      const int nc = S.ncols()[c];
       T acc = 0;
-      for (int q = 0; q < nc; ++q) acc = fma(S.Gd[(size_t)q * pcap + pz], S.x[S.ccols[q * pcap + c]], acc);
+      for (int q = 0; q < nc; ++q) acc = fma(S.Gd()[(size_t)q * pcap + pz], S.x()[S.ccols()[q * pcap + c]], acc);
       T fz = 0;
 #pragma unroll
       for (int q = 0; q < CS; ++q) {
-        const int j = S.rows[c * CS + q];
-        if (j != 0xFFFF) fz = fma(S.Fd[(size_t)c * CS * CS + r * CS + q], S.z[j], fz);
+        const int j = S.rows()[q * nc_ + c];
+        if (j != 0xFFFF) fz = fma(S.Fd()[(size_t)(r * CS + q) * nc_ + c], S.z()[j], fz);
       }
-      S.rz[i] = acc + S.s[i] - h[i] - fz;
+      S.rz()[i] = acc + S.s()[i] - h[i] - fz;
     }
     for (int k = tid; k < e; k += NT) {                            // ry = A x - b
       T acc = 0;
-      for (int j = 0; j < n; ++j) acc = fma(S.As[k * n + j], S.x[j], acc);
-      S.ry[k] = acc - b[k];
+      for (int j = 0; j < n; ++j) acc = fma(S.As()[k * n + j], S.x()[j], acc);
+      S.ry()[k] = acc - b[k];
     }
     __syncthreads();
     T q4[4] = {0, 0, 0, 0};                                        // s.z, |rz|^2, |ry|^2, |rx|^2
-    for (int i = tid; i < m; i += NT) { q4[0] += S.s[i] * S.z[i]; q4[1] += S.rz[i] * S.rz[i]; }
-    for (int i = tid; i < e; i += NT) q4[2] += S.ry[i] * S.ry[i];
-    for (int i = tid; i < n; i += NT) q4[3] += S.rx[i] * S.rx[i];
-    block_reduce<T, 4>(q4, OpSum(), T(0), S.red);
+    for (int i = tid; i < m; i += NT) { q4[0] += S.s()[i] * S.z()[i]; q4[1] += S.rz()[i] * S.rz()[i]; }
+    for (int i = tid; i < e; i += NT) q4[2] += S.ry()[i] * S.ry()[i];
+    for (int i = tid; i < n; i += NT) q4[3] += S.rx()[i] * S.rx()[i];
+    block_reduce<T, 4>(q4, OpSum(), T(0), S.red());
+    pf.lap(CPH_RESID);
     const T sz = q4[0];
     const T mu = fabs(sz / T(m));                                  // :91
     const T resid = (e > 0 ? sqrt(q4[2]) : T(0)) + sqrt(q4[1]) + sqrt(q4[3]) + T(m) * mu;   // :92-96
@@ -827,64 +998,69 @@ __device__ __forceinline__ void forward_scene(const CFwdArgs<T>& a, CSmem<T>& S,
     else { improved = resid < best; not_improved = improved ? 0 : not_improved + 1; }
     if (improved) {
       best = resid;
-      for (int i = tid; i < n; i += NT) o_x[i] = S.x[i];
-      for (int i = tid; i < m; i += NT) { o_z[i] = S.z[i]; o_s[i] = S.s[i]; }
-      for (int i = tid; i < e; i += NT) o_y[i] = S.y[i];
+      for (int i = tid; i < n; i += NT) o_x[i] = S.x()[i];
+      for (int i = tid; i < m; i += NT) { o_z[i] = S.z()[i]; o_s[i] = S.s()[i]; }
+      for (int i = tid; i < e; i += NT) o_y[i] = S.y()[i];
     }
     if (not_improved == a.not_improved_lim) { status = 1; ++it; break; }
     if (best < a.eps) { status = 2; ++it; break; }
     if (mu > T(1e100)) { status = 3; ++it; break; }
 
-    for (int i = tid; i < m; i += NT) S.d[i] = S.z[i] / S.s[i];     // :98
+    for (int i = tid; i < m; i += NT) S.d()[i] = S.z()[i] / S.s()[i];     // :98
     __syncthreads();
-    factor_kkt<T, NS, CS>(P, S, st);                               // :100
+    factor_kkt<T, NS, CS>(P, S, st, pf);                               // :100
 
     // ---- affine direction                                       :138-139   (rs = z)
-    solve_kkt<T, CS, QN>(P, S, st, S.rx, S.z, S.rz, e > 0 ? S.ry : nullptr, S.dx, S.ds, S.dz, S.dy);
+    solve_kkt<T, CS, NS>(P, S, st, pf, S.rx(), S.z(), S.rz(), e > 0 ? S.ry() : nullptr, S.dx(), S.ds(), S.dz(), S.dy());
     T stz, sts;
-    get_steps(S.z, S.dz, S.s, S.ds, m, S.red, stz, sts);
+    get_steps(S.z(), S.dz(), S.s(), S.ds(), m, S.red(), stz, sts);
     const T alpha_aff = nan_min(nan_min(stz, sts), T(1));          // :142-144
     T t3[1] = {0};
-    for (int i = tid; i < m; i += NT) t3[0] += (S.s[i] + alpha_aff * S.ds[i]) * (S.z[i] + alpha_aff * S.dz[i]);
-    block_reduce<T, 1>(t3, OpSum(), T(0), S.red);
+    for (int i = tid; i < m; i += NT) t3[0] += (S.s()[i] + alpha_aff * S.ds()[i]) * (S.z()[i] + alpha_aff * S.dz()[i]);
+    block_reduce<T, 1>(t3, OpSum(), T(0), S.red());
     const T ratio = t3[0] / sz;                                    // :146-150
     const T sig = ratio * ratio * ratio;
     const T musig = -mu * sig;                                     // :152-158
-    for (int i = tid; i < m; i += NT) S.rs2[i] = (musig + S.ds[i] * S.dz[i]) / S.s[i];
+    for (int i = tid; i < m; i += NT) S.rs2()[i] = (musig + S.ds()[i] * S.dz()[i]) / S.s()[i];
     __syncthreads();
+    pf.lap(CPH_STEP);
     // corrector: outputs land in rx / rz / ry (dead until the next residual phase)
-    solve_kkt<T, CS, QN>(P, S, st, nullptr, S.rs2, nullptr, nullptr, S.rx, S.rz, S.rs2, S.ry);
-    // NOTE: ds_c -> S.rz, dz_c -> S.rs2 (solve_kkt reads rs before it writes dz/ds of the same row)
-    for (int i = tid; i < n; i += NT) S.dx[i] += S.rx[i];          // :160-163
-    for (int i = tid; i < m; i += NT) { S.ds[i] += S.rz[i]; S.dz[i] += S.rs2[i]; }
-    for (int i = tid; i < e; i += NT) S.dy[i] += S.ry[i];
+    solve_kkt<T, CS, NS>(P, S, st, pf, nullptr, S.rs2(), nullptr, nullptr, S.rx(), S.rz(), S.rs2(), S.ry());
+    // NOTE: ds_c -> S.rz(), dz_c -> S.rs2() (solve_kkt reads rs before it writes dz/ds of the same row)
+    for (int i = tid; i < n; i += NT) S.dx()[i] += S.rx()[i];          // :160-163
+    for (int i = tid; i < m; i += NT) { S.ds()[i] += S.rz()[i]; S.dz()[i] += S.rs2()[i]; }
+    for (int i = tid; i < e; i += NT) S.dy()[i] += S.ry()[i];
     __syncthreads();
-    get_steps(S.z, S.dz, S.s, S.ds, m, S.red, stz, sts);
+    get_steps(S.z(), S.dz(), S.s(), S.ds(), m, S.red(), stz, sts);
     const T alpha = nan_min(T(0.999) * nan_min(stz, sts), T(1));   // :164-166
-    for (int i = tid; i < n; i += NT) S.x[i] += alpha * S.dx[i];   // :171-174
-    for (int i = tid; i < m; i += NT) { S.s[i] += alpha * S.ds[i]; S.z[i] += alpha * S.dz[i]; }
-    for (int i = tid; i < e; i += NT) S.y[i] += alpha * S.dy[i];
+    for (int i = tid; i < n; i += NT) S.x()[i] += alpha * S.dx()[i];   // :171-174
+    for (int i = tid; i < m; i += NT) { S.s()[i] += alpha * S.ds()[i]; S.z()[i] += alpha * S.dz()[i]; }
+    for (int i = tid; i < e; i += NT) S.y()[i] += alpha * S.dy()[i];
     __syncthreads();
+    pf.lap(CPH_STEP);
   }
   if (tid == 0) { a.status[sc] = status; a.iters[sc] = it; if (a.resid) a.resid[sc] = best; }
 }
 
 template <typename T, int NS>
-__global__ void __launch_bounds__(NT, (NS <= 3) ? 4 : ((NS <= 6) ? 2 : 1)) cond_forward_kernel(const CFwdArgs<T> a) {
+__global__ void __launch_bounds__(NT, (NS <= 6) ? 2 : 1) cond_forward_kernel(const __grid_constant__ CFwdArgs<T> a) {
   const CPlan& P = a.P;
-  CSmem<T> S;
-  S.carve(reinterpret_cast<char*>(cnd_smem), P);
+  CSmem<T> S(P);
   const int n = P.n, m = P.m, e = P.e, tid = threadIdx.x;
   __shared__ int singular_s;
   const T NANV = nan("");
+  Prof pf;
+  pf.p = a.prof ? a.prof + (size_t)blockIdx.x * CPH_COUNT : nullptr;
   for (int sc = blockIdx.x; sc < a.B; sc += gridDim.x) {
     if (tid == 0) singular_s = 0;
     __syncthreads();
+    pf.start();
     Struct st;
     const bool ok = build_structure<T>(P, S, st, a.Q + (size_t)sc * n * n, a.G + (size_t)sc * m * n,
                                        e > 0 ? a.A + (size_t)sc * e * n : nullptr, a.F + (size_t)sc * m * m,
                                        &singular_s);
     __syncthreads();
+    pf.lap(CPH_STRUCT);
     if (!ok) {
       if (singular_s) {                 // pdipm.py:361-368: the caller raises
         for (int i = tid; i < n; i += NT) a.zhat[(size_t)sc * n + i] = NANV;
@@ -898,12 +1074,12 @@ __global__ void __launch_bounds__(NT, (NS <= 3) ? 4 : ((NS <= 6) ? 2 : 1)) cond_
       continue;
     }
     switch (st.cs) {
-      case 1: forward_scene<T, NS, 1>(a, S, st, sc); break;
-      case 2: forward_scene<T, NS, 2>(a, S, st, sc); break;
-      case 3: forward_scene<T, NS, 3>(a, S, st, sc); break;
-      case 4: forward_scene<T, NS, 4>(a, S, st, sc); break;
-      case 5: forward_scene<T, NS, 5>(a, S, st, sc); break;
-      default: forward_scene<T, NS, 6>(a, S, st, sc); break;
+      case 1: forward_scene<T, NS, 1>(a, S, st, pf, sc); break;
+      case 2: forward_scene<T, NS, 2>(a, S, st, pf, sc); break;
+      case 3: forward_scene<T, NS, 3>(a, S, st, pf, sc); break;
+      case 4: forward_scene<T, NS, 4>(a, S, st, pf, sc); break;
+      case 5: forward_scene<T, NS, 5>(a, S, st, pf, sc); break;
+      default: forward_scene<T, NS, 6>(a, S, st, pf, sc); break;
     }
     __syncthreads();
   }
@@ -911,70 +1087,103 @@ __global__ void __launch_bounds__(NT, (NS <= 3) ? 4 : ((NS <= 6) ? 2 : 1)) cond_
 
 // ------------------------------------------------------------------ backward (lcp.py:37-64), one scene
 template <typename T, int NS, int CS>
-__device__ __forceinline__ void backward_scene(const CBwdArgs<T>& a, CSmem<T>& S, const Struct& st, int sc) {
-  constexpr int QN = (NS + 1) / 2;
+__device__ __forceinline__ void backward_scene(const CBwdArgs<T>& a, CSmem<T>& S, const Struct& st, Prof& pf, int sc) {
   const CPlan& P = a.P;
   const int n = P.n, m = P.m, e = P.e, tid = threadIdx.x;
   const T* zh = a.zhat + (size_t)sc * n;
   const T* lam = a.lam + (size_t)sc * m;
   const T* slk = a.slack + (size_t)sc * m;
   const T* nu = e > 0 ? a.nu + (size_t)sc * e : nullptr;
-  for (int i = tid; i < n; i += NT) { S.x[i] = zh[i]; S.rx[i] = a.g[(size_t)sc * n + i]; }
-  for (int i = tid; i < m; i += NT) { S.z[i] = lam[i]; S.s[i] = slk[i]; S.d[i] = lam[i] / slk[i]; S.rs2[i] = T(0); }   // :44
-  for (int i = tid; i < e; i += NT) S.y[i] = nu[i];
+  for (int i = tid; i < n; i += NT) { S.x()[i] = zh[i]; S.rx()[i] = a.g[(size_t)sc * n + i]; }
+  for (int i = tid; i < m; i += NT) { S.z()[i] = lam[i]; S.s()[i] = slk[i]; S.d()[i] = lam[i] / slk[i]; S.rs2()[i] = T(0); }   // :44
+  for (int i = tid; i < e; i += NT) S.y()[i] = nu[i];
   __syncthreads();
-  factor_kkt<T, NS, CS>(P, S, st);                                                      // :46
-  solve_kkt<T, CS, QN>(P, S, st, S.rx, S.rs2, nullptr, nullptr, S.dx, S.ds, S.dz, S.dy);   // :47-50
-  const T* dx = S.dx; const T* dlam = S.dz; const T* dnu = S.dy;
+  factor_kkt<T, NS, CS>(P, S, st, pf);                                                      // :46
+  solve_kkt<T, CS, NS>(P, S, st, pf, S.rx(), S.rs2(), nullptr, nullptr, S.dx(), S.ds(), S.dz(), S.dy());   // :47-50
+  const T* dx = S.dx(); const T* dlam = S.dz(); const T* dnu = S.dy();
   if (a.dp) for (int i = tid; i < n; i += NT) a.dp[(size_t)sc * n + i] = dx[i];                       // :52
   if (a.dh) for (int i = tid; i < m; i += NT) a.dh[(size_t)sc * m + i] = -dlam[i];                    // :55
   if (a.db && e > 0) for (int i = tid; i < e; i += NT) a.db[(size_t)sc * e + i] = -dnu[i];            // :58
   if (a.dG) {                                                    // :53  dlam (x) zhat + lam (x) dx
     T* o = a.dG + (size_t)sc * m * n;
-    for (int t = tid; t < m * n; t += NT) { const int i = t / n, j = t - i * n; o[t] = dlam[i] * S.x[j] + S.z[i] * dx[j]; }
+    { int i = 0, j = tid;
+      while (j >= n) { j -= n; ++i; }
+      for (size_t t = tid; t < (size_t)m * n; t += NT) {
+        o[t] = dlam[i] * S.x()[j] + S.z()[i] * dx[j];
+        j += NT;
+        while (j >= n) { j -= n; ++i; }
+      }
+    }
   }
   if (a.dF) {                                                    // :54  -dlam (x) lam
     T* o = a.dF + (size_t)sc * m * m;
-    for (int t = tid; t < m * m; t += NT) { const int i = t / m, j = t - i * m; o[t] = -(dlam[i] * S.z[j]); }
+    { int i = 0, j = tid;
+      while (j >= m) { j -= m; ++i; }
+      for (size_t t = tid; t < (size_t)m * m; t += NT) {
+        o[t] = -(dlam[i] * S.z()[j]);
+        j += NT;
+        while (j >= m) { j -= m; ++i; }
+      }
+    }
   }
   if (a.dA && e > 0) {                                           // :57
     T* o = a.dA + (size_t)sc * e * n;
-    for (int t = tid; t < e * n; t += NT) { const int i = t / n, j = t - i * n; o[t] = dnu[i] * S.x[j] + S.y[i] * dx[j]; }
+    { int i = 0, j = tid;
+      while (j >= n) { j -= n; ++i; }
+      for (size_t t = tid; t < (size_t)e * n; t += NT) {
+        o[t] = dnu[i] * S.x()[j] + S.y()[i] * dx[j];
+        j += NT;
+        while (j >= n) { j -= n; ++i; }
+      }
+    }
   }
   if (a.dQ) {                                                    // :61
     T* o = a.dQ + (size_t)sc * n * n;
-    for (int t = tid; t < n * n; t += NT) { const int i = t / n, j = t - i * n; o[t] = T(0.5) * (dx[i] * S.x[j] + S.x[i] * dx[j]); }
+    { int i = 0, j = tid;
+      while (j >= n) { j -= n; ++i; }
+      for (size_t t = tid; t < (size_t)n * n; t += NT) {
+        o[t] = T(0.5) * (dx[i] * S.x()[j] + S.x()[i] * dx[j]);
+        j += NT;
+        while (j >= n) { j -= n; ++i; }
+      }
+    }
   }
-  if (tid == 0) a.done[sc] = 1;
+  if (tid == 0 && a.done) a.done[sc] = 1;
+  __syncthreads();
+  pf.lap(CPH_GRADS);
 }
 
 template <typename T, int NS>
-__global__ void __launch_bounds__(NT, (NS <= 3) ? 4 : ((NS <= 6) ? 2 : 1)) cond_backward_kernel(const CBwdArgs<T> a) {
+__global__ void __launch_bounds__(NT, (NS <= 6) ? 2 : 1) cond_backward_kernel(const __grid_constant__ CBwdArgs<T> a) {
   const CPlan& P = a.P;
-  CSmem<T> S;
-  S.carve(reinterpret_cast<char*>(cnd_smem), P);
+  CSmem<T> S(P);
   const int n = P.n, m = P.m, e = P.e, tid = threadIdx.x;
   __shared__ int singular_s;
+  Prof pf;
+  pf.p = a.prof ? a.prof + (size_t)blockIdx.x * CPH_COUNT : nullptr;
   for (int sc = blockIdx.x; sc < a.B; sc += gridDim.x) {
+    if (a.only && !a.only[sc]) continue;
     if (tid == 0) singular_s = 0;
     __syncthreads();
+    pf.start();
     Struct st;
     const bool ok = build_structure<T>(P, S, st, a.Q + (size_t)sc * n * n, a.G + (size_t)sc * m * n,
                                        e > 0 ? a.A + (size_t)sc * e * n : nullptr, a.F + (size_t)sc * m * m,
                                        &singular_s);
     __syncthreads();
+    pf.lap(CPH_STRUCT);
     if (!ok) {
-      if (tid == 0) a.done[sc] = 0;
+      if (tid == 0 && a.done) a.done[sc] = 0;
       __syncthreads();
       continue;
     }
     switch (st.cs) {
-      case 1: backward_scene<T, NS, 1>(a, S, st, sc); break;
-      case 2: backward_scene<T, NS, 2>(a, S, st, sc); break;
-      case 3: backward_scene<T, NS, 3>(a, S, st, sc); break;
-      case 4: backward_scene<T, NS, 4>(a, S, st, sc); break;
-      case 5: backward_scene<T, NS, 5>(a, S, st, sc); break;
-      default: backward_scene<T, NS, 6>(a, S, st, sc); break;
+      case 1: backward_scene<T, NS, 1>(a, S, st, pf, sc); break;
+      case 2: backward_scene<T, NS, 2>(a, S, st, pf, sc); break;
+      case 3: backward_scene<T, NS, 3>(a, S, st, pf, sc); break;
+      case 4: backward_scene<T, NS, 4>(a, S, st, pf, sc); break;
+      case 5: backward_scene<T, NS, 5>(a, S, st, pf, sc); break;
+      default: backward_scene<T, NS, 6>(a, S, st, pf, sc); break;
     }
     __syncthreads();
   }

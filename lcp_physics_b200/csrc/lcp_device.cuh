@@ -47,8 +47,8 @@ struct Team {
   __device__ __forceinline__ static Team cta() { Team t; t.tid = threadIdx.x; t.nt = blockDim.x; t.bar = 0; return t; }
 };
 
-// Block-wide reduction of up to 4 values at once; result broadcast to all threads.
-// red: shared scratch of >= 4*32 elements. Ends with a barrier that makes `red` reusable.
+// Block-wide reduction of up to 6 values at once; result broadcast to all threads.
+// red: shared scratch of >= NV*32 elements. Ends with a barrier that makes `red` reusable.
 template <typename T, int NV, typename Op>
 __device__ __forceinline__ void block_reduce(T (&v)[NV], Op op, T ident, T* red, const Team& tm) {
   const int lane = tm.tid & 31, warp = tm.tid >> 5, nw = (tm.nt + 31) >> 5;

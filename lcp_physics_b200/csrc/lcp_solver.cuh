@@ -969,6 +969,7 @@ struct BwdArgs {
   const T* Rsave;             // nullptr (recompute R) or the matrices saved by the forward pass
   long long* prof;
   const int* skip;            // nullptr or [B]: non-zero = gradients already written by lcp_condensed.cuh
+  int* bad;                   // nullptr or [B]: set to 1 when the solve produced non-finite dx / dlam (LU broke down)
 };
 
 template <typename T, int MODE>
@@ -1004,6 +1005,13 @@ __global__ void __launch_bounds__(512, 1) lcp_backward_kernel(const BwdArgs<T> a
     solve_kkt(c, off(v.rx), off(v.rs2), -1, -1, off(v.dxa), off(v.dsa), off(v.dza), off(v.dya));   // :47-50
     prof_lap(c, PH_SOLVE);
     const T* dx = v.dxa; const T* dlam = v.dza; const T* dnu = v.dya;
+    if (a.bad) {
+      int nf = 0;
+      for (int i = tid; i < n; i += NT) nf |= !isfinite((double)dx[i]);
+      for (int i = tid; i < m; i += NT) nf |= !isfinite((double)dlam[i]);
+      nf = __syncthreads_or(nf);
+      if (tid == 0) a.bad[sc] = nf ? 1 : 0;
+    }
     if (a.dp) for (int i = tid; i < n; i += NT) a.dp[(size_t)sc * n + i] = dx[i];                       // :52
     if (a.dh) for (int i = tid; i < m; i += NT) a.dh[(size_t)sc * m + i] = -dlam[i];                    // :55
     if (a.db && e > 0) for (int i = tid; i < e; i += NT) a.db[(size_t)sc * e + i] = -dnu[i];            // :58

@@ -55,6 +55,7 @@ struct lcpb200_handle_s {
   cudaStream_t streams[NSLOT] = {nullptr, nullptr};
   DevBuf d_in[7], d_out[6], d_bwd[16];
   long long* prof = nullptr;      // optional per-CTA phase cycle counters [NSLOT*max_grid][PH_COUNT]
+  long long* cprof = nullptr;     // same for the condensed kernels [NSLOT*cond_grid][CPH_COUNT]
   DevBuf d_R;                     // host pipeline: R of every scene, kept for backward_host
   int retained_B = 0;             // scenes whose inputs/results forward_host left on the device
   bool retained_R = false;        // ... and whether R of those scenes is in d_R
@@ -168,17 +169,17 @@ static int make_cplan(lcpb200_handle_s* h) {
   for (int k = 4; k >= 0; --k) if (16 * sizes[k] >= N) NS = sizes[k];
   C.n = n; C.m = m; C.e = e; C.N = N; C.NS = NS; C.NP = 16 * NS;
   C.pcap = (m + 7) & ~7;
+  C.flags = getenv("LCPB200_COND_FLAGS") ? atoi(getenv("LCPB200_COND_FLAGS")) : 3;
   const int dyn_max = h->smem_optin - 1024;
-  const int target = NS <= 3 ? 4 : (NS <= 6 ? 2 : 1);           // CTAs per SM the kernels are bounded for
+  const int target = NS <= 6 ? 2 : 1;                              // CTAs per SM the kernels are bounded for
   // shared memory per SM: 228 KB, 1 KB reserved per resident CTA
   const int per_cta_target = (228 * 1024) / target - 1024 - 64;
-  cnd::CSmem<T> sm;
   int best = -1;
   for (int want = target; want >= 1 && best < 0; --want) {
     const int lim = std::min(dyn_max, want == target ? per_cta_target : (228 * 1024) / want - 1024 - 64);
     for (int mult = cnd::CSMAX; mult >= 1; --mult) {            // capacity of W / Fd: mult * pcap elements
       C.wcap = mult * C.pcap;
-      const size_t bytes = sm.carve(reinterpret_cast<char*>(16), C);
+      const size_t bytes = cnd::carve_plan(C, (int)sizeof(T));
       if ((long long)bytes <= lim) { best = (int)bytes; break; }
       if (mult <= 4) break;                                     // the engine's fd = 2 blocks need 4
     }
@@ -244,6 +245,7 @@ extern "C" int lcpb200_destroy(lcpb200_handle_t h) {
   cudaSetDevice(h->device);
   if (h->ws) cudaFree(h->ws);
   if (h->prof) cudaFree(h->prof);
+  if (h->cprof) cudaFree(h->cprof);
   for (auto& s : h->streams) if (s) cudaStreamDestroy(s);
   for (auto& b : h->d_in) b.release();
   for (auto& b : h->d_out) b.release();
@@ -293,6 +295,7 @@ static int launch_forward(lcpb200_handle_s* h, int slot, int B, const void* Q, c
     c.zhat = (T*)zhat; c.nu = (T*)nu; c.lam = (T*)lam; c.slack = (T*)slack; c.resid = (T*)resid;
     c.status = status; c.iters = iters;
     c.eps = (T)eps; c.not_improved_lim = not_improved_lim; c.max_iter = max_iter;
+    c.prof = h->cprof ? h->cprof + (size_t)slot * h->cond_grid * cnd::CPH_COUNT : nullptr;
     const int cgrid = std::min(B, h->cond_grid);
 #define CALL_FWD(NSV) cnd::launch_cond_forward_t<T, NSV>(c, cgrid, st)
     const cudaError_t ce = LCPB200_NS_DISPATCH(h->cplan.NS, CALL_FWD);
@@ -327,22 +330,31 @@ static int launch_backward(lcpb200_handle_s* h, int slot, int B, const void* Q, 
                            const void* F, const void* zhat, const void* nu, const void* lam, const void* slack,
                            const void* g, void* dQ, void* dp, void* dG, void* dh, void* dA, void* db, void* dF,
                            const void* Rsave, unsigned flags, cudaStream_t st) {
-  // fp32: condensed-KKT backward first. fp64 stays on the dual form: at the fp64 round-off floor
-  // (lambda, s ~ 1e-16, d = lambda/s spanning 1e+-16) the condensed matrix loses dx (DESIGN.md "Parity").
-  const bool cond = h->cplan.ok != 0 && sizeof(T) == 4 && !getenv("LCPB200_DUAL_BACKWARD");
-  int* done = nullptr;
-  if (cond) {
+  // fp32: condensed-KKT backward first, the dual form only for the scenes it flags as unstructured.
+  // fp64: the dual form first -- at the fp64 round-off floor (lambda, s ~ 1e-16, d = lambda/s spanning
+  // 1e+-16) the condensed matrix loses dx (DESIGN.md "Parity") -- and the condensed kernel only as a rescue
+  // for scenes on which the dual LU (pivoting restricted to its diagonal blocks) broke down (non-finite dx).
+  const bool have_cond = h->cplan.ok != 0;
+  const bool cond_first = have_cond && sizeof(T) == 4 && !getenv("LCPB200_DUAL_BACKWARD");
+  int* flagbuf = nullptr;
+  if (have_cond) {
     CK(h->d_flag[slot].ensure(sizeof(int) * (size_t)B));
-    done = (int*)h->d_flag[slot].p;
-    cnd::CBwdArgs<T> c;
+    flagbuf = (int*)h->d_flag[slot].p;
+  }
+  cnd::CBwdArgs<T> c;
+  if (have_cond) {
     c.P = h->cplan;
     c.B = B;
     c.Q = (const T*)Q; c.G = (const T*)G; c.A = (const T*)A; c.F = (const T*)F;
     c.zhat = (const T*)zhat; c.nu = (const T*)nu; c.lam = (const T*)lam; c.slack = (const T*)slack;
     c.g = (const T*)g;
     c.dQ = (T*)dQ; c.dp = (T*)dp; c.dG = (T*)dG; c.dh = (T*)dh; c.dA = (T*)dA; c.db = (T*)db; c.dF = (T*)dF;
-    c.done = done;
-    const int cgrid = std::min(B, h->cond_grid);
+    c.done = cond_first ? flagbuf : nullptr;
+    c.only = cond_first ? nullptr : flagbuf;
+    c.prof = h->cprof ? h->cprof + (size_t)slot * h->cond_grid * cnd::CPH_COUNT : nullptr;
+  }
+  const int cgrid = std::min(B, std::max(h->cond_grid, 1));
+  if (cond_first) {
 #define CALL_BWD(NSV) cnd::launch_cond_backward_t<T, NSV>(c, cgrid, st)
     const cudaError_t ce = LCPB200_NS_DISPATCH(h->cplan.NS, CALL_BWD);
 #undef CALL_BWD
@@ -357,8 +369,9 @@ static int launch_backward(lcpb200_handle_s* h, int slot, int B, const void* Q, 
   a.g = (const T*)g;
   a.dQ = (T*)dQ; a.dp = (T*)dp; a.dG = (T*)dG; a.dh = (T*)dh; a.dA = (T*)dA; a.db = (T*)db; a.dF = (T*)dF;
   a.flags = flags;
-  a.Rsave = (h->cplan.ok != 0) ? nullptr : (const T*)Rsave;    // R is only formed when the forward ran on the dual form
-  a.skip = done;
+  a.Rsave = have_cond ? nullptr : (const T*)Rsave;    // R is only formed when the forward ran on the dual form
+  a.skip = cond_first ? flagbuf : nullptr;
+  a.bad = (have_cond && !cond_first) ? flagbuf : nullptr;
   a.ws = (T*)h->ws + (size_t)slot * h->plan.ws_per_cta * h->ws_ctas;
   a.prof = h->prof ? h->prof + (size_t)slot * h->max_grid * PH_COUNT : nullptr;
   const int grid = std::min(B, h->ws_ctas);
@@ -367,6 +380,12 @@ static int launch_backward(lcpb200_handle_s* h, int slot, int B, const void* Q, 
                          : mode == 1 ? launch_backward_t<T, 1>(a, grid, st)
                                      : launch_backward_t<T, 2>(a, grid, st);
   CK(le);
+  if (have_cond && !cond_first) {
+#define CALL_BWD(NSV) cnd::launch_cond_backward_t<T, NSV>(c, cgrid, st)
+    const cudaError_t ce = LCPB200_NS_DISPATCH(h->cplan.NS, CALL_BWD);
+#undef CALL_BWD
+    CK(ce);
+  }
   return 0;
 }
 
@@ -419,22 +438,30 @@ extern "C" int lcpb200_backward(lcpb200_handle_t h, int B, const void* Q, const 
 
 extern "C" int lcpb200_profile(lcpb200_handle_t h, int enable, long long* out) {
   // Development aid: per-phase SM cycle counters (thread 0 of every CTA), summed over CTAs.
-  // enable = 1 allocates + zeroes the counters, 0 frees them; `out` (PH_COUNT = 14 values:
-  // prefactor, load T, LU, KKT solves, residuals, step rules) receives the current sums.
+  // enable = 1 allocates + zeroes the counters, 0 frees them; `out` receives 24 values: the 14
+  // dual-form phases (see the header) followed by the 10 condensed-kernel phases.
   if (!h) return fail("null handle");
   CK(cudaSetDevice(h->device));
   const size_t cnt = (size_t)lcpb200_handle_s::NSLOT * h->max_grid * PH_COUNT;
+  const size_t ccnt = (size_t)lcpb200_handle_s::NSLOT * std::max(h->cond_grid, 1) * cnd::CPH_COUNT;
   if (out) {
-    for (int i = 0; i < PH_COUNT; ++i) out[i] = 0;
+    for (int i = 0; i < PH_COUNT + cnd::CPH_COUNT; ++i) out[i] = 0;
     if (h->prof) {
       std::vector<long long> tmp(cnt);
       CK(cudaMemcpy(tmp.data(), h->prof, cnt * sizeof(long long), cudaMemcpyDeviceToHost));
       for (size_t i = 0; i < cnt; ++i) out[i % PH_COUNT] += tmp[i];
     }
+    if (h->cprof) {
+      std::vector<long long> tmp(ccnt);
+      CK(cudaMemcpy(tmp.data(), h->cprof, ccnt * sizeof(long long), cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < ccnt; ++i) out[PH_COUNT + i % cnd::CPH_COUNT] += tmp[i];
+    }
   }
   if (enable && !h->prof) CK(cudaMalloc(&h->prof, cnt * sizeof(long long)));
-  if (enable) CK(cudaMemset(h->prof, 0, cnt * sizeof(long long)));
+  if (enable && !h->cprof) CK(cudaMalloc(&h->cprof, ccnt * sizeof(long long)));
+  if (enable) { CK(cudaMemset(h->prof, 0, cnt * sizeof(long long))); CK(cudaMemset(h->cprof, 0, ccnt * sizeof(long long))); }
   if (!enable && h->prof) { cudaFree(h->prof); h->prof = nullptr; }
+  if (!enable && h->cprof) { cudaFree(h->cprof); h->cprof = nullptr; }
   return 0;
 }
 

@@ -11,8 +11,10 @@ scenes of `nb` circles with `nc` contacts and `fd` friction directions:
     p = M v + dt f,   h = [(Jc v) * restitution, 0, 0]
     A = identity rows pinning body 0 (a TotalConstraint, constraints.py:176-192)
 
-Everything is generated on the CPU with a `torch.Generator` so the same seed
-gives bit-identical inputs in the build container and on the GPU box.
+Everything is generated on the CPU with a `torch.Generator`: the random draws are
+reproducible across hosts, the derived arithmetic (normals, Jacobians) only to the
+last bit or two (different BLAS code paths) -- fixtures that must be exact store
+their inputs (tests/golden/make_seeded_golden.py).
 Also exposes the contact/body structure-of-arrays the assembly kernel consumes.
 """
 import math

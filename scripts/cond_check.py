@@ -50,7 +50,10 @@ if __name__ == "__main__":
     # timing at the BASELINE size
     B = 4096
     inp = [t.cuda() for t in make_scenes(B, 32, 64, fd=2, e=0, dtype=torch.float32, seed=7)]
-    for rep in range(3):
+    hd = _lib.get_handle(torch.float32, 96, 256, 0, 0)
+    for rep in range(4):
+        if rep == 3:
+            hd.profile(True)
         torch.cuda.synchronize(); t0 = time.time()
         out = solve_forward(*inp, max_iter=10)
         torch.cuda.synchronize(); t1 = time.time()
@@ -59,6 +62,22 @@ if __name__ == "__main__":
         torch.cuda.synchronize(); t2 = time.time()
         print("cfg3 B=4096: forward %.2f ms  backward %.2f ms  status %s iters %.2f" % (
             (t1 - t0) * 1e3, (t2 - t1) * 1e3, sorted(set(out[4].cpu().tolist())), out[5].float().mean()), flush=True)
+    pr = hd.profile(False)
+    tot = sum(v for k, v in pr.items() if k.startswith("c_"))
+    print("condensed phases (share of counted cycles, cycles per scene):")
+    for k, v in pr.items():
+        if k.startswith("c_") and v:
+            print("   %-18s %5.1f %%  %9.0f" % (k, 100.0 * v / tot, v / B))
+    for Bs in (148, 296):
+        sub = [t[:Bs].contiguous() for t in inp]
+        solve_forward(*sub, max_iter=10)
+        hd.profile(True)
+        torch.cuda.synchronize(); t0 = time.time()
+        solve_forward(*sub, max_iter=10)
+        torch.cuda.synchronize(); t1 = time.time()
+        pr = hd.profile(False)
+        print("forward only, B=%d (%.2f ms): cycles per scene:" % (Bs, (t1 - t0) * 1e3),
+              " ".join("%s=%.0f" % (k[2:], v / Bs) for k, v in pr.items() if k.startswith("c_") and v))
     B = 1024
     inp = [t.cuda() for t in make_scenes(B, 16, 32, fd=3, e=0, dtype=torch.float64, seed=7)]
     for rep in range(3):

@@ -10,7 +10,31 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def golden_names():
     return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-                  if not n.startswith("world_"))
+                  if not n.startswith("world_") and not n.startswith("seeded_"))
+
+
+def seeded_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "seeded_*.npz")))
+
+
+def load_seeded_golden(name):
+    """Fixtures of tests/golden/make_seeded_golden.py: outputs of the unmodified reference on 48 seeded scenes
+    at a BASELINE shape, with the inputs stored in packed form (non-zero pattern once, values per scene).
+    Returns (fp64 inputs, {"f64": outputs, "f32": outputs}, max_iter, dl_dzhat)."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    B = int(z["kwargs"][0])
+    inp = []
+    for k in "Q p G h A b F".split():
+        if "in_" + k + "_idx" in z.files:
+            shape = tuple(int(v) for v in z["in_" + k + "_shape"])
+            flat = torch.zeros(B, int(np.prod(shape)), dtype=torch.float64)
+            flat[:, torch.from_numpy(z["in_" + k + "_idx"].astype(np.int64))] = torch.from_numpy(z["in_" + k + "_val"])
+            inp.append(flat.reshape((B,) + shape))
+        else:
+            inp.append(torch.tensor([], dtype=torch.float64))          # e == 0: 1-D empty A, b (engines.py:59-60)
+    out = {tag: {k[len(tag) + 1:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(tag + "_")}
+           for tag in ("f64", "f32")}
+    return tuple(inp), out, int(z["max_iter"]), torch.from_numpy(z["dl_dzhat"])
 
 
 def load_golden(name, dtype=torch.float64):
