@@ -118,7 +118,8 @@ class Handle:
             pass
 
 
-_handles = {}
+_handles = {}          # insertion-ordered: least recently used first
+_MAX_HANDLES = 32
 
 
 def clear_handles():
@@ -126,12 +127,15 @@ def clear_handles():
     _handles.clear()
 
 
-def get_handle(dtype, n, m, e, device_index):
-    key = (dtype, n, m, e, device_index)
-    h = _handles.get(key)
+def get_handle(dtype, n, m, e, device_index, stream=0):
+    """One handle (plan + workspace) per (dtype, n, m, e, device, stream): the library's contract is one
+    stream at a time per handle, so CUDA callers are keyed by their current stream and the host-buffer
+    path (which runs on the handle's private streams) by stream = "host". LRU, at most 32 handles."""
+    key = (dtype, n, m, e, device_index, stream)
+    h = _handles.pop(key, None)
     if h is None:
-        if len(_handles) >= 32:
+        while len(_handles) >= _MAX_HANDLES:
             _handles.pop(next(iter(_handles)))
         h = Handle(dtype, n, m, e, device_index)
-        _handles[key] = h
+    _handles[key] = h
     return h

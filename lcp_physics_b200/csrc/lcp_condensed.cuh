@@ -459,7 +459,7 @@ __device__ __forceinline__ void comp_inverse(const CPlan& P, CSmem<T>& S, const 
 
 // out_c = W_c * in_c for every component, in place in S.scr (one thread per (component, row))
 template <typename T, int CS>
-__device__ __forceinline__ void comp_apply(CSmem<T>& S, const Struct& st) {
+__device__ __forceinline__ void comp_apply(CSmem<T>& S, const Struct& st, bool trans = false) {
   const int nc_ = st.ncomp;                       // positions are slot-major: pos(c, r) = r * ncomp + c
   const int npos = nc_ * CS;
   const int sh = st.sh, cmask = (1 << sh) - 1, tot = CS << sh;
@@ -471,7 +471,7 @@ __device__ __forceinline__ void comp_apply(CSmem<T>& S, const Struct& st) {
     if (t < tot && c < nc_) {
       double a = 0.0;
 #pragma unroll
-      for (int q = 0; q < CS; ++q) a = fma(S.W()[(size_t)(r * CS + q) * nc_ + c], S.scr()[q * nc_ + c], a);
+      for (int q = 0; q < CS; ++q) a = fma(S.W()[(size_t)(trans ? (q * CS + r) : (r * CS + q)) * nc_ + c], S.scr()[q * nc_ + c], a);
       val[u] = a;
     }
   }
@@ -642,7 +642,7 @@ template <int NS> struct SolveLayout {
 
 // K (shared, column major) -> registers -> LU -> factors back to the K region in the solve layout.
 template <int NS>
-__device__ __noinline__ void factor_K(int o_K, int o_rdiag) {
+__device__ __noinline__ void factor_K(int o_K, int o_rdiag, bool trans) {
   constexpr int NP = 16 * NS, QN = SolveLayout<NS>::QN;
   int tid_;                                          // read %tid.x once (opaque to the compiler: no re-reads in the loops)
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_));
@@ -658,18 +658,26 @@ __device__ __noinline__ void factor_K(int o_K, int o_rdiag) {
   int step = 0;
   LuPhases<NS, 0>::run(a, o_K, o_rdiag, step, ti, tj);
   __syncthreads();                                   // rdiag complete, broadcast buffers dead
+  // trans (exact-adjoint backward): K^T = U^T L^T = L' U' with L'[i][k] = U[k][i] / u_kk and
+  // U'[i][k] / u'_kk = u_ii L[k][i] / u_kk, i.e. entry (i, k) of the solve layout receives a[k][i] / u_kk:
+  // the roles of the row and column index of a are swapped, the scale is the ROW's reciprocal pivot.
   int rowpart[NS];
+  double rrow[NS];
 #pragma unroll
-  for (int r = 0; r < NS; ++r) { const int i = 16 * r + ti; rowpart[r] = (i % QN) * QN * 32 + i / QN; }
+  for (int r = 0; r < NS; ++r) {
+    const int i = 16 * r + ti;
+    rowpart[r] = trans ? (i / QN) * QN * QN * 32 + (i % QN) * 32 : (i % QN) * QN * 32 + i / QN;
+    rrow[r] = rdiag[i];
+  }
 #pragma unroll
   for (int c = 0; c < NS; ++c) {
     const int j = 16 * c + tj;
     const double rj = rdiag[j];
-    const int colpart = (j / QN) * QN * QN * 32 + (j % QN) * 32;
+    const int colpart = trans ? (j % QN) * QN * 32 + j / QN : (j / QN) * QN * QN * 32 + (j % QN) * 32;
 #pragma unroll
     for (int r = 0; r < NS; ++r) {
       const int i = 16 * r + ti;
-      K[colpart + rowpart[r]] = (i != j) ? a[r][c] * rj : a[r][c];
+      K[colpart + rowpart[r]] = (i != j) ? a[r][c] * (trans ? rrow[r] : rj) : a[r][c];
     }
   }
   __syncthreads();
@@ -776,7 +784,8 @@ __device__ __noinline__ void solve_warp(int o_K, int o_rdiag, int o_bx) {
 // Inputs (nullptr == zero vector): rx[n], rs[m], rz[m], ry[e]; outputs dx[n], ds[m], dz[m], dy[e].
 template <typename T, int CS, int NS>
 __device__ __forceinline__ void solve_kkt(const CPlan& P, CSmem<T>& S, const Struct& st, Prof& pf, const T* rx,
-                                          const T* rs, const T* rz, const T* ry, T* dx, T* ds, T* dz, T* dy) {
+                                          const T* rs, const T* rz, const T* ry, T* dx, T* ds, T* dz, T* dy,
+                                          bool trans = false) {
   const int nc_ = st.ncomp;                       // positions are slot-major: pos(c, r) = r * ncomp + c
   const int n = P.n, e = P.e, N = P.N, NP = P.NP, tid = threadIdx.x, pcap = P.pcap;
   const int npos = st.ncomp * CS;
@@ -788,7 +797,7 @@ __device__ __forceinline__ void solve_kkt(const CPlan& P, CSmem<T>& S, const Str
     S.scr()[p] = t;
   }
   __syncthreads();
-  comp_apply<T, CS>(S, st);
+  comp_apply<T, CS>(S, st, trans);
   __syncthreads();
   for (int a = tid; a < NP; a += NT) {
     double acc = 0.0;
@@ -825,7 +834,7 @@ __device__ __forceinline__ void solve_kkt(const CPlan& P, CSmem<T>& S, const Str
     S.scr()[p] = t;
   }
   __syncthreads();
-  comp_apply<T, CS>(S, st);
+  comp_apply<T, CS>(S, st, trans);
   __syncthreads();
   for (int p = tid; p < npos; p += NT) {
     const int i = S.rows()[p];
@@ -843,13 +852,13 @@ __device__ __forceinline__ void solve_kkt(const CPlan& P, CSmem<T>& S, const Str
 
 // d is in S.d(): W, K, LU
 template <typename T, int NS, int CS>
-__device__ __forceinline__ void factor_kkt(const CPlan& P, CSmem<T>& S, const Struct& st, Prof& pf) {
+__device__ __forceinline__ void factor_kkt(const CPlan& P, CSmem<T>& S, const Struct& st, Prof& pf, bool trans = false) {
   comp_inverse<T, CS>(P, S, st);
   __syncthreads();
   pf.lap(CPH_WINV);
   assemble_K<T, NS, CS>(P, S, st);
   pf.lap(CPH_ASSEMBLE);
-  factor_K<NS>(P.o_K, P.o_rdiag);
+  factor_K<NS>(P.o_K, P.o_rdiag, trans);
   pf.lap(CPH_LU);
 }
 
@@ -901,6 +910,7 @@ struct CBwdArgs {
   T *dQ, *dp, *dG, *dh, *dA, *db, *dF;
   int* done;                  // nullptr or [B]: 1 = gradients written here, 0 = scene left to the dual-form kernel
   const int* only;            // nullptr or [B]: process only the scenes flagged non-zero (rescue pass after the dual form)
+  unsigned flags;             // LCPB200_BWD_*: bit 0 = exact adjoint (transposed KKT system: K^T, W^T)
   long long* prof;
 };
 
@@ -1098,8 +1108,9 @@ __device__ __forceinline__ void backward_scene(const CBwdArgs<T>& a, CSmem<T>& S
   for (int i = tid; i < m; i += NT) { S.z()[i] = lam[i]; S.s()[i] = slk[i]; S.d()[i] = lam[i] / slk[i]; S.rs2()[i] = T(0); }   // :44
   for (int i = tid; i < e; i += NT) S.y()[i] = nu[i];
   __syncthreads();
-  factor_kkt<T, NS, CS>(P, S, st, pf);                                                      // :46
-  solve_kkt<T, CS, NS>(P, S, st, pf, S.rx(), S.rs2(), nullptr, nullptr, S.dx(), S.ds(), S.dz(), S.dy());   // :47-50
+  const bool exact = (a.flags & 1u) != 0;
+  factor_kkt<T, NS, CS>(P, S, st, pf, exact);                                               // :46
+  solve_kkt<T, CS, NS>(P, S, st, pf, S.rx(), S.rs2(), nullptr, nullptr, S.dx(), S.ds(), S.dz(), S.dy(), exact);   // :47-50
   const T* dx = S.dx(); const T* dlam = S.dz(); const T* dnu = S.dy();
   if (a.dp) for (int i = tid; i < n; i += NT) a.dp[(size_t)sc * n + i] = dx[i];                       // :52
   if (a.dh) for (int i = tid; i < m; i += NT) a.dh[(size_t)sc * m + i] = -dlam[i];                    // :55

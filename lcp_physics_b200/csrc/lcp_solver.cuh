@@ -83,6 +83,7 @@ struct SceneCtx {
   bool Rsaved;                // R points at a matrix saved by the forward pass (read-only)
   bool qdiag;                 // Q is diagonal: Q^{-1} v is an element-wise product with Vecs::qinv
   bool t_prefetched;          // R is already on its way into T's shared region (prefetch_T)
+  bool transF;                // backward, exact adjoint: R is formed with F^T (the transposed KKT system)
   bool f_ell;                 // F has <= 4 non-zeros in every row: F z uses the ELL copy (Fell_v / Fell_i)
   T* Fell_v; int* Fell_i;     // [4][m] values / column indices (L2 workspace)
   bool g_ell_built;           // build_g_ell already ran for this scene (inside prefactor, from the staged copy)
@@ -210,7 +211,7 @@ __device__ __forceinline__ void gemv_cols_v(const T* __restrict__ A, int lda, in
 // consecutive rows, conflict-free. R and F are the L2/HBM arrays [m,m].
 template <typename T>
 __device__ __forceinline__ void gram_diag(const T* __restrict__ Gs, int ldg, const T* qi, const T* __restrict__ F,
-                                          T* __restrict__ R, int m, int n) {
+                                          T* __restrict__ R, int m, int n, bool transF = false) {
   using V = typename VecOf<T>::type;
   constexpr int VC = VecOf<T>::VC;
   constexpr int TR = 8, TC = 8;
@@ -257,7 +258,7 @@ __device__ __forceinline__ void gram_diag(const T* __restrict__ Gs, int ldg, con
 #pragma unroll
       for (int c = 0; c < TC; ++c) {
         const int j = cb + 8 * c;
-        if (j < m) R[(size_t)i * m + j] = F[(size_t)i * m + j] + acc[r][c];
+        if (j < m) R[(size_t)i * m + j] = (transF ? F[(size_t)j * m + i] : F[(size_t)i * m + j]) + acc[r][c];
       }
     }
   }
@@ -449,16 +450,16 @@ __device__ __noinline__ bool prefactor(SceneCtx<T, MODE>& c, int* flag) {
         for (int t = tid; t < m * n; t += NT) { const int i = t / n, j = t - i * n; Gs[(size_t)i * ldgs + j] = c.Gsrc[t]; }
       }
       __syncthreads();
-      gram_diag<T>(Gs, ldgs, qd, c.F, c.R, m, n);
+      gram_diag<T>(Gs, ldgs, qd, c.F, c.R, m, n, c.transF);
       build_g_ell(c, Gs, ldgs);                                  // while the staged copy is still there
     } else {
       __syncthreads();
-      gram_diag<T>(c.G, c.ldG, qd, c.F, c.R, m, n);
+      gram_diag<T>(c.G, c.ldG, qd, c.F, c.R, m, n, c.transF);
     }
   } else {
     // X = Q^{-1} G^T ; R = G X + F                                 :378-379
     gemm_tiled<T, true>(c.X, m, c.Qi, c.ldQi, c.G, c.ldG, n, m, n, T(1), T(0));
-    for (int t = tid; t < m * m; t += NT) c.R[t] = c.F[t];
+    for (int t = tid; t < m * m; t += NT) { const int i = t / m, j = t - i * m; c.R[t] = c.transF ? c.F[(size_t)j * m + i] : c.F[t]; }
     __syncthreads();
     gemm_tiled<T, false>(c.R, m, c.G, c.ldG, c.X, m, m, m, n, T(1), T(1));
   }
@@ -758,7 +759,7 @@ __device__ void setup_ctx(SceneCtx<T, MODE>& c, const Plan& P, T* sm, T* ws, int
   c.Gr_v = ws + P.w_Gell; c.Gr_i = reinterpret_cast<int*>(ws + P.w_Gell + (long long)8 * P.m);
   c.Gc_v = ws + P.w_Gell + (long long)16 * P.m; c.Gc_i = reinterpret_cast<int*>(ws + P.w_Gell + (long long)16 * P.m + (long long)32 * P.n);
   c.g_ell = false; c.g_ell_built = false;
-  c.Rsaved = false; c.qdiag = false; c.t_prefetched = false; c.stage_ld = P.stage_ld; c.Gsrc = nullptr;
+  c.Rsaved = false; c.transF = false; c.qdiag = false; c.t_prefetched = false; c.stage_ld = P.stage_ld; c.Gsrc = nullptr;
   c.lu_flag = lu_flag;
   c.prof = prof ? prof + (size_t)blockIdx.x * PH_COUNT : nullptr;
   Vecs<T> v = c.vecs();
@@ -994,7 +995,8 @@ __global__ void __launch_bounds__(512, 1) lcp_backward_kernel(const BwdArgs<T> a
     const T* lam = a.lam + (size_t)sc * m;
     const T* slk = a.slack + (size_t)sc * m;
     const T* nu = e > 0 ? a.nu + (size_t)sc * e : nullptr;
-    if (a.Rsave) { c.R = const_cast<T*>(a.Rsave) + (size_t)sc * m * m; c.Rsaved = true; }
+    c.transF = (a.flags & 1u) != 0;      // LCPB200_BWD_EXACT_ADJOINT (the saved R holds F, so it is not used then)
+    if (a.Rsave && !c.transF) { c.R = const_cast<T*>(a.Rsave) + (size_t)sc * m * m; c.Rsaved = true; }
     prefactor(c, &flag);     // singular Q was already reported by the forward pass
     prof_lap(c, PH_PREFACTOR);
     for (int i = tid; i < n; i += NT) { v.x[i] = zh[i]; v.rx[i] = a.g[(size_t)sc * n + i]; }

@@ -25,6 +25,19 @@ static int fail(const std::string& s) { g_err = s; return 1; }
                   std::to_string(__LINE__) + ")");                                               \
   } while (0)
 
+// Restores the caller's current device when an entry point returns (the library switches to the handle's).
+struct DeviceGuard {
+  int prev = -1;
+  bool armed = false;
+  cudaError_t set(int device) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return e;
+    armed = (prev != device);
+    return armed ? cudaSetDevice(device) : cudaSuccess;
+  }
+  ~DeviceGuard() { if (armed) cudaSetDevice(prev); }
+};
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -206,7 +219,8 @@ extern "C" int lcpb200_create(int dtype, int n, int m, int e, int device, lcpb20
   *out = nullptr;
   if (dtype != LCPB200_F32 && dtype != LCPB200_F64) return fail("dtype must be LCPB200_F32 or LCPB200_F64");
   if (n <= 0 || m <= 0 || e < 0) return fail("need n > 0, m > 0, e >= 0");
-  CK(cudaSetDevice(device));
+  DeviceGuard dg_;
+  CK(dg_.set(device));
   lcpb200_handle_s* h = new (std::nothrow) lcpb200_handle_s();
   if (!h) return fail("out of host memory");
   h->dtype = dtype; h->n = n; h->m = m; h->e = e; h->device = device;
@@ -242,7 +256,8 @@ static int ensure_ws(lcpb200_handle_s* h, int B) {
 
 extern "C" int lcpb200_destroy(lcpb200_handle_t h) {
   if (!h) return 0;
-  cudaSetDevice(h->device);
+  DeviceGuard dg_;
+  dg_.set(h->device);
   if (h->ws) cudaFree(h->ws);
   if (h->prof) cudaFree(h->prof);
   if (h->cprof) cudaFree(h->cprof);
@@ -351,6 +366,7 @@ static int launch_backward(lcpb200_handle_s* h, int slot, int B, const void* Q, 
     c.dQ = (T*)dQ; c.dp = (T*)dp; c.dG = (T*)dG; c.dh = (T*)dh; c.dA = (T*)dA; c.db = (T*)db; c.dF = (T*)dF;
     c.done = cond_first ? flagbuf : nullptr;
     c.only = cond_first ? nullptr : flagbuf;
+    c.flags = flags;
     c.prof = h->cprof ? h->cprof + (size_t)slot * h->cond_grid * cnd::CPH_COUNT : nullptr;
   }
   const int cgrid = std::min(B, std::max(h->cond_grid, 1));
@@ -409,7 +425,8 @@ extern "C" int lcpb200_forward(lcpb200_handle_t h, int B, const void* Q, const v
                                int32_t* status, int32_t* iters, void* resid, void* Rsave, void* stream) {
   if (int rc = check_fwd_args(h, B, Q, p, G, hv, A, b, F, zhat, nu, lam, slack, status, iters, max_iter)) return rc;
   if (B == 0) return 0;
-  CK(cudaSetDevice(h->device));
+  DeviceGuard dg_;
+  CK(dg_.set(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   return h->dtype == LCPB200_F32
              ? launch_forward<float>(h, 0, B, Q, p, G, hv, A, b, F, eps, not_improved_lim, max_iter, zhat, nu, lam,
@@ -426,10 +443,11 @@ extern "C" int lcpb200_backward(lcpb200_handle_t h, int B, const void* Q, const 
   if (B < 0) return fail("B < 0");
   if (!Q || !G || !F || !zhat || !lam || !slack || !g) return fail("Q, G, F, zhat, lam, slack, dl_dzhat must be non-NULL");
   if (h->e > 0 && (!A || !nu)) return fail("A and nu must be non-NULL when e > 0");
-  if (flags != LCPB200_BWD_BUG_COMPATIBLE)
-    return fail("only LCPB200_BWD_BUG_COMPATIBLE is implemented (the reference's backward, lcp.py:37-64)");
+  if (flags != LCPB200_BWD_BUG_COMPATIBLE && flags != LCPB200_BWD_EXACT_ADJOINT)
+    return fail("flags must be LCPB200_BWD_BUG_COMPATIBLE or LCPB200_BWD_EXACT_ADJOINT");
   if (B == 0) return 0;
-  CK(cudaSetDevice(h->device));
+  DeviceGuard dg_;
+  CK(dg_.set(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   return h->dtype == LCPB200_F32
              ? launch_backward<float>(h, 0, B, Q, G, A, F, zhat, nu, lam, slack, g, dQ, dp, dG, dh, dA, db, dF, Rsave, flags, st)
@@ -441,7 +459,8 @@ extern "C" int lcpb200_profile(lcpb200_handle_t h, int enable, long long* out) {
   // enable = 1 allocates + zeroes the counters, 0 frees them; `out` receives 24 values: the 14
   // dual-form phases (see the header) followed by the 10 condensed-kernel phases.
   if (!h) return fail("null handle");
-  CK(cudaSetDevice(h->device));
+  DeviceGuard dg_;
+  CK(dg_.set(h->device));
   const size_t cnt = (size_t)lcpb200_handle_s::NSLOT * h->max_grid * PH_COUNT;
   const size_t ccnt = (size_t)lcpb200_handle_s::NSLOT * std::max(h->cond_grid, 1) * cnd::CPH_COUNT;
   if (out) {
@@ -487,7 +506,8 @@ extern "C" int lcpb200_forward_host(lcpb200_handle_t h, int B, const void* Q, co
                                     void* slack, int32_t* status, int32_t* iters, void* resid) {
   if (int rc = check_fwd_args(h, B, Q, p, G, hv, A, b, F, zhat, nu, lam, slack, status, iters, max_iter)) return rc;
   if (B == 0) return 0;
-  CK(cudaSetDevice(h->device));
+  DeviceGuard dg_;
+  CK(dg_.set(h->device));
   if (int rc = ensure_streams(h)) return rc;
   const size_t w = h->dtype == LCPB200_F32 ? 4 : 8;
   const size_t n = h->n, m = h->m, e = h->e;
@@ -561,9 +581,11 @@ extern "C" int lcpb200_backward_host(lcpb200_handle_t h, int B, const void* Q, c
     if (!G || !F || !zhat || !lam || !slack || !g) return fail("Q, G, F, zhat, lam, slack, dl_dzhat must be non-NULL");
     if (h->e > 0 && (!A || !nu)) return fail("A and nu must be non-NULL when e > 0");
   }
-  if (flags != LCPB200_BWD_BUG_COMPATIBLE) return fail("only LCPB200_BWD_BUG_COMPATIBLE is implemented");
+  if (flags != LCPB200_BWD_BUG_COMPATIBLE && flags != LCPB200_BWD_EXACT_ADJOINT)
+    return fail("flags must be LCPB200_BWD_BUG_COMPATIBLE or LCPB200_BWD_EXACT_ADJOINT");
   if (B == 0) return 0;
-  CK(cudaSetDevice(h->device));
+  DeviceGuard dg_;
+  CK(dg_.set(h->device));
   if (int rc = ensure_streams(h)) return rc;
   const size_t w = h->dtype == LCPB200_F32 ? 4 : 8;
   const size_t n = h->n, m = h->m, e = h->e;

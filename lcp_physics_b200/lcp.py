@@ -43,7 +43,9 @@ def _sizes(Q, p, G, h, A, b, F):
     if not (e > 0 or m > 0):
         raise AssertionError("need neq > 0 or nineq > 0")   # lcp.py:25
     if m == 0:
-        raise ValueError("lcp_physics_b200 needs at least one inequality row")
+        # lcp.py:25 lets neq > 0, nineq == 0 through, but the reference's pdipm then fails (IndexError in
+        # its first get_step): there is no behaviour to mirror
+        raise ValueError("lcp_physics_b200 needs at least one inequality row (the reference crashes on nineq == 0)")
     exp = {"Q": (B, n, n), "p": (B, n), "h": (B, m), "F": (B, m, m)}
     for name, t in (("Q", Q), ("p", p), ("h", h), ("F", F)):
         if tuple(t.shape) != exp[name]:
@@ -75,7 +77,8 @@ def solve_forward(Q, p, G, h, A, b, F, eps=1e-12, not_improved_lim=3, max_iter=1
             raise ValueError("all LCP inputs must share dtype and device")
     on_host = dev.type != "cuda"
     dev_index = torch.cuda.current_device() if on_host else dev.index
-    hd = _lib.get_handle(dtype, n, m, e, dev_index)
+    hd = _lib.get_handle(dtype, n, m, e, dev_index,
+                         "host" if on_host else torch.cuda.current_stream(dev).cuda_stream)
     if out is not None:
         zhat, nu, lam, slack, status, iters, resid = out
     else:
@@ -100,10 +103,14 @@ def solve_forward(Q, p, G, h, A, b, F, eps=1e-12, not_improved_lim=3, max_iter=1
     return zhat, nu, lam, slack, status, iters, resid
 
 
-def solve_backward(Q, G, A, F, zhat, nu, lam, slack, dl_dzhat, need=(True,) * 7, out=None, saved=None):
+def solve_backward(Q, G, A, F, zhat, nu, lam, slack, dl_dzhat, need=(True,) * 7, out=None, saved=None,
+                   exact_adjoint=False):
     """Raw backward (lcp.py:37-64): returns (dQ, dp, dG, dh, dA, db, dF); entries
     not needed (or dA/db when e == 0) are None. `out`: preallocated results.
-    `saved`: the dict filled by solve_forward(save=...) for the same inputs."""
+    `saved`: the dict filled by solve_forward(save=...) for the same inputs.
+    `exact_adjoint`: False = the reference's behaviour (it re-uses the UN-transposed KKT
+    factorisation, which is the true adjoint only when F == 0 -- SURVEY.md F6); True = the
+    transposed system (F^T in place of F inside the KKT solve), the exact gradient."""
     _lib.require_cuda()
     lib = _lib.load()
     B, m, n = G.shape
@@ -111,7 +118,8 @@ def solve_backward(Q, G, A, F, zhat, nu, lam, slack, dl_dzhat, need=(True,) * 7,
     dtype, dev = G.dtype, G.device
     on_host = dev.type != "cuda"
     dev_index = torch.cuda.current_device() if on_host else dev.index
-    hd = _lib.get_handle(dtype, n, m, e, dev_index)
+    hd = _lib.get_handle(dtype, n, m, e, dev_index,
+                         "host" if on_host else torch.cuda.current_stream(dev).cuda_stream)
     mk = lambda *shape: torch.empty(*shape, dtype=dtype, device=dev)
     shapes = [(B, n, n), (B, n), (B, m, n), (B, m), (B, e, n), (B, e), (B, m, m)]
     outs = []
@@ -133,9 +141,9 @@ def solve_backward(Q, G, A, F, zhat, nu, lam, slack, dl_dzhat, need=(True,) * 7,
         else:
             in_ptrs = [_lib.ptr(t) for t in ins]
         hd.host_generation += 1
-        _lib.check(lib.lcpb200_backward_host(hd.raw, B, *in_ptrs, *[_lib.ptr(t) for t in outs], 0))
+        _lib.check(lib.lcpb200_backward_host(hd.raw, B, *in_ptrs, *[_lib.ptr(t) for t in outs], 1 if exact_adjoint else 0))
     else:
-        args = [hd.raw, B] + [_lib.ptr(t) for t in ins] + [_lib.ptr(t) for t in outs] + [None, 0]
+        args = [hd.raw, B] + [_lib.ptr(t) for t in ins] + [_lib.ptr(t) for t in outs] + [None, 1 if exact_adjoint else 0]
         with torch.cuda.device(dev):
             _lib.check(lib.lcpb200_backward(*args, _stream_ptr(dev)))
     return tuple(outs)
@@ -155,6 +163,7 @@ class _LCPFn(torch.autograd.Function):
             print(resid.max())
         e = A.shape[1] if A.dim() > 1 else 0
         ctx.e = e
+        ctx.exact_adjoint = bool(getattr(opts, "exact_adjoint", False))
         ctx.save_for_backward(zhat, Q, G, A if e > 0 else None, F, nu, lam, slack)
         ctx.AB_proto = (A, b)
         opts.nus, opts.lams, opts.slacks = nu, lam, slack          # lcp.py:29 stashes these on self
@@ -166,7 +175,7 @@ class _LCPFn(torch.autograd.Function):
         zhat, Q, G, A, F, nu, lam, slack = ctx.saved_tensors
         need = list(ctx.needs_input_grad[:7])
         dQ, dp, dG, dh, dA, db, dF = solve_backward(Q, G, A, F, zhat, nu, lam, slack, dl_dzhat, need,
-                                                    saved=ctx.saved_state)
+                                                    saved=ctx.saved_state, exact_adjoint=ctx.exact_adjoint)
         return dQ, dp, dG, dh, dA, db, dF, None
 
 
@@ -176,7 +185,9 @@ class LCPFunction:
     Mirrors `lcp_physics.lcp.lcp.LCPFunction(eps, verbose, not_improved_lim,
     max_iter)(Q, p, G, h, A, b, F)` -- reference lcp/lcp.py:12-35."""
 
-    def __init__(self, eps=1e-12, verbose=-1, not_improved_lim=3, max_iter=10):
+    def __init__(self, eps=1e-12, verbose=-1, not_improved_lim=3, max_iter=10, exact_adjoint=False):
+        # exact_adjoint is an extension (SURVEY.md f-4): False reproduces the reference's gradients
+        self.exact_adjoint = exact_adjoint
         self.eps = eps
         self.verbose = verbose
         self.not_improved_lim = not_improved_lim

@@ -400,3 +400,19 @@ def lcp_backward_from_saved(inputs, zhat, nus, lams, slacks, dl_dzhat, pivot=Tru
     res.zhat, res.nus, res.lams, res.slacks = zhat, nus, lams, slacks
     res.inputs = (Q, p, G, h, A if e > 0 else None, b if e > 0 else None, F)
     return lcp_backward(res, dl_dzhat)
+
+
+def lcp_backward_exact_from_saved(inputs, zhat, nus, lams, slacks, dl_dzhat, pivot=True):
+    """EXTENSION, not in the reference: the exact adjoint. Differentiating the KKT
+    conditions  Q x + p + G^T lam + A^T nu = 0,  G x + s - h - F lam = 0,  lam o s = 0,  A x = b  and
+    solving the TRANSPOSED Jacobian system gives the reference's formulas (lcp.py:52-63) with ONE change: the
+    KKT solve uses F^T in place of F (for F = 0 the two coincide, which is why qpth's formulas are exact
+    there). Used only to cross-check the CUDA exact-adjoint path; tests also check it against finite
+    differences of the forward solve."""
+    Q, p, G, h, A, b, F = inputs
+    nb, n, m, e = _sizes(G, A)
+    res = LCPOracleResult()
+    res.state = prefactor(Q, G, F.transpose(1, 2).contiguous(), A if e > 0 else None, pivot=pivot)
+    res.zhat, res.nus, res.lams, res.slacks = zhat, nus, lams, slacks
+    res.inputs = (Q, p, G, h, A if e > 0 else None, b if e > 0 else None, F)
+    return lcp_backward(res, dl_dzhat)

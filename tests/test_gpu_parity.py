@@ -366,6 +366,51 @@ def test_autograd_through_lcpfunction_matches_oracle(dtype):
         assert rel_err(leaf.grad.cpu(), r).max() < gtol, nm
 
 
+@pytest.mark.parametrize("e", [0, 3])
+def test_exact_adjoint_matches_finite_differences_fp64(e):
+    """LCPB200_BWD_EXACT_ADJOINT: gradients of l = g . zhat against central finite differences of
+    the converged forward solve, along random directions of p, h, G and F (restricted to their non-zero
+    patterns). The reference's (bug-compatible) gradients fail the same check when F != 0."""
+    from lcp_physics_b200 import solve_forward, solve_backward
+    from lcp_physics_b200.scenes import make_scenes
+    from oracle import pdipm_oracle as po
+    inp = make_scenes(6, 5, 6, fd=2, e=e, dtype=torch.float64, seed=33)
+    Q, p, G, h, A, b, F = inp
+    gen = torch.Generator().manual_seed(7)
+    g = torch.randn(6, 15, generator=gen, dtype=torch.float64)
+    kw = dict(max_iter=40, eps=1e-10)
+
+    def loss(args):
+        z = solve_forward(*_cuda(args), **kw)[0].cpu()
+        return (z * g).sum(1)
+
+    out = solve_forward(*_cuda(inp), **kw)
+    assert (out[6] < 1e-8).all()                                  # converged (best residual)
+    dev = _cuda(inp)
+    nu = out[1] if e > 0 else None
+    exact = solve_backward(dev[0], dev[2], dev[4] if e else None, dev[6], out[0], nu, out[2], out[3], g.cuda(),
+                           exact_adjoint=True)
+    compat = solve_backward(dev[0], dev[2], dev[4] if e else None, dev[6], out[0], nu, out[2], out[3], g.cuda())
+    ora = po.lcp_backward_exact_from_saved(inp, out[0].cpu(), nu.cpu() if e else None, out[2].cpu(), out[3].cpu(), g)
+    eps = 1e-5
+    worst_exact, worst_compat = 0.0, 0.0
+    for k, name in ((1, "dp"), (3, "dh"), (2, "dG"), (6, "dF")):
+        d = torch.randn(inp[k].shape, generator=gen, dtype=torch.float64) * (inp[k] != 0 if k in (2, 6) else 1.0)
+        plus = [t.clone() for t in inp]; minus = [t.clone() for t in inp]
+        plus[k] += eps * d; minus[k] -= eps * d
+        fd = (loss(plus) - loss(minus)) / (2 * eps)
+        an_exact = (exact[k].cpu() * d).flatten(1).sum(1)
+        an_compat = (compat[k].cpu() * d).flatten(1).sum(1)
+        scale = fd.abs().max()
+        worst_exact = max(worst_exact, float((an_exact - fd).abs().max() / scale))
+        worst_compat = max(worst_compat, float((an_compat - fd).abs().max() / scale))
+        # CUDA vs the oracle's restatement of the same (transposed) system; the state is converged, so
+        # d = lambda/s spans 1e+-10 and dlam (dh, dG, dF) carries the KKT conditioning noise of tests/test_oracle.py
+        assert rel_err(exact[k].cpu(), ora[k]).max() < (1e-6 if name == "dp" else 2e-3), name
+    assert worst_exact < 2e-3, worst_exact
+    assert worst_compat > 5 * worst_exact, (worst_compat, worst_exact)
+
+
 def test_host_buffers_equal_device_buffers():
     """CPU tensors go through lcpb200_forward_host / backward_host (chunked copy+solve pipeline), including the
     retained-state backward (Q == NULL) that bench.py's e2e leg uses."""
