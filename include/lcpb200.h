@@ -34,8 +34,12 @@
  *     RuntimeError (pdipm.py:361-368).
  *   - Scenes are independent: per-scene termination and per-scene get_step
  *     maximum (<= 1.5e-12 rel from the batch-coupled reference).
- *   - Factorisations are pivot-free, as the reference's own CUDA path
- *     (pdipm.py:18 `pivot=not x.is_cuda`).
+ *   - Two kernel families. Scenes with the engine's structure (diagonal Q, sparse
+ *     G, block-sparse F) are solved through the condensed n x n KKT system, formed / factored in fp64
+ *     without pivoting (it is quasi-definite). Other scenes fall back, per scene, to the dual m x m
+ *     form of the reference with threshold partial pivoting restricted to the LU's diagonal blocks
+ *     (the reference pivots over whole columns on CPU tensors and not at all on CUDA tensors,
+ *     pdipm.py:18 `pivot=not x.is_cuda`).
  *   - One stream at a time per handle (the handle owns the workspace).
  */
 #ifndef LCPB200_H
@@ -48,7 +52,7 @@
 extern "C" {
 #endif
 
-#define LCPB200_VERSION 100
+#define LCPB200_VERSION 200
 
 #define LCPB200_F32 0
 #define LCPB200_F64 1
@@ -79,7 +83,9 @@ size_t lcpb200_workspace_bytes(lcpb200_handle_t h);
 int lcpb200_describe(lcpb200_handle_t h, char* buf, size_t len);
 
 /* Development aid: per-phase SM cycle counters of the solver kernels, summed over CTAs.
- * enable=1 allocates/zeroes them, 0 frees; out (may be NULL) receives 14 values:
+ * enable=1 allocates/zeroes them, 0 frees; out (may be NULL) receives 24 values: the 14 dual-form phases below
+ * followed by the 10 condensed-kernel phases {structure, block inverses, assembly of K, LU, solve: right-hand
+ * side, solve: substitution, solve: back-substitution of the multipliers, residuals, step rules, gradients}:
  * {prefactor, load T, LU, KKT solves, residuals, step rules,
  *  LU: diagonal blocks (look-ahead warp), LU: panel solves, LU: trailing updates,
  *  LU: diagonal-block inverses, number of diagonal blocks with row interchanges, number of
@@ -159,6 +165,38 @@ int lcpb200_assemble_backward(int dtype, int B, int nb, int nc, double dt,
                               void* dmass, void* dinertia, void* dv, void* dfext,
                               void* dnormal, void* dp1, void* dp2,
                               void* dmu, void* drestitution, void* stream);
+
+/* Fused engine entry points (lcpb200_assemble_solve). They replace, in ONE kernel per pass,
+ *   mode 0: PdipmEngine.solve_dynamics' LCP (physics/engines.py:50-76) incl. the assembly of
+ *           world.py:144-234:  zhat = LCP(M, M v + dt f, [Jc; Jf; 0], [(Jc v) rest, 0, 0], A, b, F(E, mu));
+ *           the engine returns -zhat (engines.py:76);
+ *   mode 1: PdipmEngine.post_stabilization's LCP (physics/engines.py:80-116):
+ *           zhat = LCP(M, 0, Jc, (Jc v)(1 - rest), A, b, 0).
+ * Inputs are the contact structure-of-arrays of lcpb200_assemble (+ optional equality rows A[B,e,n], b[B,e],
+ * e.g. World.Je()); nothing dense is written to or read from HBM. The handle must have been created with
+ * n = 3 nb, m = 4 nc (mode 0) or nc (mode 1), and n + e <= 128 (the condensed-KKT kernels). A scene whose
+ * contact topology the kernel cannot take (a contact of a body with itself, > 16 contact rows per degree of
+ * freedom) gets status -100 and no result: assemble it with lcpb200_assemble and call lcpb200_forward.
+ * lcpb200_engine_backward: the chain rule through the assembly applied to the factored gradients of
+ * lcp.py:52-63 (dG = dlam (x) zhat + lam (x) dx, ...): gradients w.r.t. the contact list, any may be NULL. */
+int lcpb200_engine_forward(lcpb200_handle_t h, int B, int nb, int nc, int mode, double dt,
+                           const void* mass, const void* inertia, const void* v, const void* fext,
+                           const void* normal, const void* p1, const void* p2,
+                           const int32_t* body1, const int32_t* body2,
+                           const void* mu, const void* restitution, const void* A, const void* b,
+                           double eps, int not_improved_lim, int max_iter,
+                           void* zhat, void* nu, void* lam, void* slack,
+                           int32_t* status, int32_t* iters, void* resid, void* stream);
+int lcpb200_engine_backward(lcpb200_handle_t h, int B, int nb, int nc, int mode, double dt,
+                            const void* mass, const void* inertia, const void* v, const void* fext,
+                            const void* normal, const void* p1, const void* p2,
+                            const int32_t* body1, const int32_t* body2,
+                            const void* mu, const void* restitution, const void* A,
+                            const void* zhat, const void* nu, const void* lam, const void* slack,
+                            const void* dl_dzhat,
+                            void* dmass, void* dinertia, void* dv, void* dfext,
+                            void* dnormal, void* dp1, void* dp2, void* dmu, void* drestitution,
+                            void* dA, void* db, unsigned flags, void* stream);
 
 #ifdef __cplusplus
 }

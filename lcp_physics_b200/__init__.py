@@ -3,3 +3,4 @@
 from .lcp import LCPFunction, solve_forward, solve_backward  # noqa: F401
 
 __all__ = ["LCPFunction", "solve_forward", "solve_backward"]
+# fused engine path (contact list in, solution out): lcp_physics_b200.engines.engine_solve / B200PdipmEngine

@@ -387,6 +387,130 @@ __device__ __noinline__ bool build_structure(const CPlan& P, CSmem<T>& S, Struct
   return true;
 }
 
+// ------------------------------------------------------------------ engine path: structure from the contact list
+// The fused entry points (lcpb200_engine_forward / _backward) hand the kernels the contact
+// structure-of-arrays the engine holds (world.py:139-234, engines.py:50-116) instead of dense Q, G, F:
+// the components, their columns and values are known in closed form, nothing dense is read or written.
+template <typename T>
+struct EngineSoA {
+  const T *mass, *inertia, *v, *fext;         // [B,nb] [B,nb] [B,n] [B,n];  mass == nullptr: dense inputs
+  const T *normal, *p1, *p2;                  // [B,nc,2]
+  const T *mu, *rest;                         // [B,nc]
+  const int32_t *b1, *b2;                     // [nc] contact topology, shared by the batch
+  int nb, nc;
+  int mode;                                   // 0: solve_dynamics (engines.py:50-76), 1: post_stabilization (engines.py:80-116)
+  T dt;
+  T *p_s, *h_s;                               // [B,n], [B,m]: p and h of every scene (written here, read by the solver)
+};
+
+// Jacobian row of contact c along direction (dx, dy), restricted to the six columns of its two bodies
+// (world.py:172-184): body1 gets [p1 x d, d], body2 the negated [p2 x d, d].
+template <typename T>
+__device__ __forceinline__ void contact_row(T p1x, T p1y, T p2x, T p2y, T dx, T dy, T (&r1)[3], T (&r2)[3]) {
+  r1[0] = p1x * dy - p1y * dx; r1[1] = dx; r1[2] = dy;
+  r2[0] = -(p2x * dy - p2y * dx); r2[1] = -dx; r2[2] = -dy;
+}
+
+template <typename T>
+__device__ __noinline__ bool build_structure_soa(const CPlan& P, CSmem<T>& S, Struct& st, const EngineSoA<T>& e_,
+                                                 int sc, const T* __restrict__ A, int* singular) {
+  const int n = P.n, m = P.m, e = P.e, tid = threadIdx.x, pcap = P.pcap;
+  const int nb = e_.nb, nc = e_.nc, cs = e_.mode == 0 ? 4 : 1;
+  char* sb = reinterpret_cast<char*>(S.K());
+  unsigned short* cl_tmp = reinterpret_cast<unsigned short*>(sb);                      // [LMAX][n]
+  int* cl_cnt = reinterpret_cast<int*>(sb + al16((size_t)LMAX * n * 2));               // [n]
+  if (n != 3 * nb || m != cs * nc || nc * cs > pcap || nc * cs * cs > P.wcap) return false;
+  const T* mass = e_.mass + (size_t)sc * nb;
+  const T* inertia = e_.inertia + (size_t)sc * nb;
+  const T* v = e_.v + (size_t)sc * n;
+  const T* normal = e_.normal + (size_t)sc * nc * 2;
+  const T* p1 = e_.p1 + (size_t)sc * nc * 2;
+  const T* p2 = e_.p2 + (size_t)sc * nc * 2;
+  T* ps = e_.p_s + (size_t)sc * n;
+  T* hs = e_.h_s + (size_t)sc * m;
+  int bad = 0;
+  for (int j = tid; j < n; j += NT) {
+    const int body = j / 3;
+    const T q = (j - 3 * body == 0) ? inertia[body] : mass[body];          // world.py:57-61, bodies.py:44-47
+    S.qd()[j] = q;
+    if (!(q != T(0) && isfinite((double)q))) bad |= 2;
+    ps[j] = e_.mode == 0 ? q * v[j] + e_.dt * e_.fext[(size_t)sc * n + j] : T(0);      // engines.py:32 / :109
+    cl_cnt[j] = 0;
+  }
+  for (int t = tid; t < e * n; t += NT) S.As()[t] = A[t];
+  st.ncomp = nc; st.cs = cs;
+  st.sh = 0;
+  while ((1 << st.sh) < nc) ++st.sh;
+  for (int t = tid; t < UC * pcap; t += NT) { S.Gd()[t] = T(0); S.ccols()[t] = 0; }
+  for (int t = tid; t < nc * cs * cs; t += NT) S.Fd()[t] = T(0);
+  __syncthreads();
+  for (int c = tid; c < nc; c += NT) {
+    const int b1 = e_.b1[c], b2 = e_.b2[c];
+    if (b1 == b2 || b1 < 0 || b2 < 0 || b1 >= nb || b2 >= nb) { bad |= 1; continue; }
+    const int lo = min(b1, b2), hi = max(b1, b2);
+    const int o1 = b1 < b2 ? 0 : 3, o2 = 3 - o1;                   // slots of body1 / body2 in the sorted column list
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      S.ccols()[q * pcap + c] = (unsigned char)(3 * lo + q);
+      S.ccols()[(3 + q) * pcap + c] = (unsigned char)(3 * hi + q);
+    }
+    S.ncols()[c] = 6;
+    const T nx = normal[2 * c], ny = normal[2 * c + 1];
+    const T p1x = p1[2 * c], p1y = p1[2 * c + 1], p2x = p2[2 * c], p2y = p2[2 * c + 1];
+    T r1[3], r2[3];
+    contact_row<T>(p1x, p1y, p2x, p2y, nx, ny, r1, r2);            // Jc row
+    const T jv = r1[0] * v[3 * b1] + r1[1] * v[3 * b1 + 1] + r1[2] * v[3 * b1 + 2] +
+                 r2[0] * v[3 * b2] + r2[1] * v[3 * b2 + 1] + r2[2] * v[3 * b2 + 2];
+    const T rc = e_.rest[(size_t)sc * nc + c];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { S.Gd()[(size_t)(o1 + q) * pcap + c] = r1[q]; S.Gd()[(size_t)(o2 + q) * pcap + c] = r2[q]; }
+    S.rows()[c] = (unsigned short)c;
+    S.posof()[c] = (unsigned short)c;
+    if (e_.mode == 0) {
+      hs[c] = jv * rc;                                             // engines.py:53,74
+      contact_row<T>(p1x, p1y, p2x, p2y, ny, -nx, r1, r2);         // Jf rows: +- left_orthogonal(n)  (world.py:186-211)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        S.Gd()[(size_t)(o1 + q) * pcap + nc + c] = r1[q];      S.Gd()[(size_t)(o2 + q) * pcap + nc + c] = r2[q];
+        S.Gd()[(size_t)(o1 + q) * pcap + 2 * nc + c] = -r1[q]; S.Gd()[(size_t)(o2 + q) * pcap + 2 * nc + c] = -r2[q];
+      }
+      const int rw[4] = {c, nc + 2 * c, nc + 2 * c + 1, 3 * nc + c};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { S.rows()[r * nc + c] = (unsigned short)rw[r]; S.posof()[rw[r]] = (unsigned short)(r * nc + c); }
+      hs[nc + 2 * c] = T(0); hs[nc + 2 * c + 1] = T(0); hs[3 * nc + c] = T(0);
+      // F = [[0,0,0],[0,0,E],[mu,-E^T,0]]  (engines.py:69-73): rows/cols {c, f1, f2, gamma} of the component
+      S.Fd()[(size_t)(1 * 4 + 3) * nc + c] = T(1);
+      S.Fd()[(size_t)(2 * 4 + 3) * nc + c] = T(1);
+      S.Fd()[(size_t)(3 * 4 + 0) * nc + c] = e_.mu[(size_t)sc * nc + c];
+      S.Fd()[(size_t)(3 * 4 + 1) * nc + c] = T(-1);
+      S.Fd()[(size_t)(3 * 4 + 2) * nc + c] = T(-1);
+    } else {
+      hs[c] = jv + jv * -rc;                                       // engines.py:90
+    }
+    // column lists: arrival order, ranked below
+    for (int q = 0; q < 6; ++q) {
+      const int a = q < 3 ? 3 * lo + q : 3 * hi + q - 3;
+      const int slot = atomicAdd(&cl_cnt[a], 1);
+      if (slot < LMAX) cl_tmp[slot * n + a] = (unsigned short)(c * 8 + q); else bad |= 1;
+    }
+  }
+  const int anybad = __syncthreads_or(bad);
+  if (anybad & 2) { *singular = 1; return false; }
+  if (anybad & 1) return false;
+  for (int t = tid; t < n * LMAX; t += NT) {
+    const int a = t % n, l = t / n, cnt = cl_cnt[a];
+    if (l < cnt) {
+      const int val = cl_tmp[l * n + a];
+      int rank = 0;
+      for (int u = 0; u < cnt; ++u) rank += (cl_tmp[u * n + a] < val);
+      S.clist()[rank * n + a] = (unsigned short)val;
+    }
+    if (l == 0) S.clcnt()[a] = (unsigned char)cnt;
+  }
+  __syncthreads();
+  return true;
+}
+
 __device__ __forceinline__ double rcp64_fast(double x) {
   // MUFU.RCP64H seed (>= 20 bits) + 2 Newton steps; exact division outside the seed's range
   double r;
@@ -899,6 +1023,7 @@ struct CFwdArgs {
   T eps;
   int not_improved_lim, max_iter;
   long long* prof;            // nullptr or [grid][CPH_COUNT]
+  EngineSoA<T> soa;           // soa.mass != nullptr: structure, p and h come from the contact list (Q, G, F unused)
 };
 
 template <typename T>
@@ -911,6 +1036,8 @@ struct CBwdArgs {
   int* done;                  // nullptr or [B]: 1 = gradients written here, 0 = scene left to the dual-form kernel
   const int* only;            // nullptr or [B]: process only the scenes flagged non-zero (rescue pass after the dual form)
   unsigned flags;             // LCPB200_BWD_*: bit 0 = exact adjoint (transposed KKT system: K^T, W^T)
+  EngineSoA<T> soa;           // engine path: gradients w.r.t. the contact list instead of dense ones
+  T *dmass, *dinertia, *dv, *dfext, *dnormal, *dp1, *dp2, *dmu, *drest;   // engine path outputs (any may be nullptr)
   long long* prof;
 };
 
@@ -1066,9 +1193,10 @@ __global__ void __launch_bounds__(NT, (NS <= 6) ? 2 : 1) cond_forward_kernel(con
     __syncthreads();
     pf.start();
     Struct st;
-    const bool ok = build_structure<T>(P, S, st, a.Q + (size_t)sc * n * n, a.G + (size_t)sc * m * n,
-                                       e > 0 ? a.A + (size_t)sc * e * n : nullptr, a.F + (size_t)sc * m * m,
-                                       &singular_s);
+    const bool ok = a.soa.mass
+        ? build_structure_soa<T>(P, S, st, a.soa, sc, e > 0 ? a.A + (size_t)sc * e * n : nullptr, &singular_s)
+        : build_structure<T>(P, S, st, a.Q + (size_t)sc * n * n, a.G + (size_t)sc * m * n,
+                             e > 0 ? a.A + (size_t)sc * e * n : nullptr, a.F + (size_t)sc * m * m, &singular_s);
     __syncthreads();
     pf.lap(CPH_STRUCT);
     if (!ok) {
@@ -1112,6 +1240,92 @@ __device__ __forceinline__ void backward_scene(const CBwdArgs<T>& a, CSmem<T>& S
   factor_kkt<T, NS, CS>(P, S, st, pf, exact);                                               // :46
   solve_kkt<T, CS, NS>(P, S, st, pf, S.rx(), S.rs2(), nullptr, nullptr, S.dx(), S.ds(), S.dz(), S.dy(), exact);   // :47-50
   const T* dx = S.dx(); const T* dlam = S.dz(); const T* dnu = S.dy();
+  if (a.soa.mass) {
+    // Engine path: the chain rule through the assembly (world.py:144-234, engines.py:50-116) applied to the
+    // FACTORED gradients of lcp.py:52-63 -- dG = dlam (x) zhat + lam (x) dx, dF = -dlam (x) lam, dh = -dlam,
+    // dQ = sym(dx (x) zhat), dp = dx -- evaluated only at the entries the assembly writes.
+    const EngineSoA<T>& E = a.soa;
+    const int nc = E.nc, nb = E.nb;
+    const T* v = E.v + (size_t)sc * n;
+    const T* zh_ = S.x(); const T* lm = S.z();
+    for (int c = tid; c < nc; c += NT) {
+      const size_t ic = (size_t)sc * nc + c;
+      const T nx = E.normal[ic * 2], ny = E.normal[ic * 2 + 1];
+      const T p1x = E.p1[ic * 2], p1y = E.p1[ic * 2 + 1], p2x = E.p2[ic * 2], p2y = E.p2[ic * 2 + 1];
+      const int j1 = 3 * E.b1[c], j2 = 3 * E.b2[c];
+      const T rc = E.rest[ic];
+      const T dhc = -dlam[c] * (E.mode == 0 ? T(1) : T(1));      // dh = -dlam  (:55)
+      T gnx = 0, gny = 0, g1x = 0, g1y = 0, g2x = 0, g2y = 0, jcv = 0;
+      const int nrows = E.mode == 0 ? 3 : 1;
+      const int rows_[3] = {c, nc + 2 * c, nc + 2 * c + 1};
+      const T dxs[3] = {nx, ny, -ny}, dys[3] = {ny, -nx, nx};
+      for (int q = 0; q < nrows; ++q) {
+        const T ddx_ = dxs[q], ddy_ = dys[q];
+        const int i = rows_[q];
+        T g[6];
+        for (int t = 0; t < 3; ++t) {
+          g[t] = dlam[i] * zh_[j1 + t] + lm[i] * dx[j1 + t];      // dG[i][j1+t]  (:53)
+          g[3 + t] = dlam[i] * zh_[j2 + t] + lm[i] * dx[j2 + t];
+        }
+        if (q == 0) {
+          const T row[6] = {p1x * ddy_ - p1y * ddx_, ddx_, ddy_, -(p2x * ddy_ - p2y * ddx_), -ddx_, -ddy_};
+          for (int t = 0; t < 3; ++t) jcv += row[t] * v[j1 + t] + row[3 + t] * v[j2 + t];
+          const T hs_ = E.mode == 0 ? rc : (T(1) - rc);            // h_c = (Jc v) rest  |  (Jc v)(1 - rest)
+          for (int t = 0; t < 3; ++t) { g[t] += dhc * hs_ * v[j1 + t]; g[3 + t] += dhc * hs_ * v[j2 + t]; }
+        }
+        const T gdx = -p1y * g[0] + g[1] + p2y * g[3] - g[4];
+        const T gdy = p1x * g[0] + g[2] - p2x * g[3] - g[5];
+        g1x += ddy_ * g[0]; g1y += -ddx_ * g[0];
+        g2x += -ddy_ * g[3]; g2y += ddx_ * g[3];
+        if (q == 0) { gnx += gdx; gny += gdy; }
+        else if (q == 1) { gny += gdx; gnx += -gdy; }               // dir1 = (ny, -nx)
+        else { gny += -gdx; gnx += gdy; }                           // dir2 = (-ny, nx)
+      }
+      if (a.dnormal) { a.dnormal[ic * 2] = gnx; a.dnormal[ic * 2 + 1] = gny; }
+      if (a.dp1) { a.dp1[ic * 2] = g1x; a.dp1[ic * 2 + 1] = g1y; }
+      if (a.dp2) { a.dp2[ic * 2] = g2x; a.dp2[ic * 2 + 1] = g2y; }
+      if (a.drest) a.drest[ic] = E.mode == 0 ? dhc * jcv : -dhc * jcv;
+      if (a.dmu) a.dmu[ic] = E.mode == 0 ? -(dlam[3 * nc + c] * lm[c]) : T(0);     // dF[gamma_c][c]  (:54)
+    }
+    for (int j = tid; j < n; j += NT) {
+      const int body = j / 3, comp = j - 3 * body;
+      const T md = comp == 0 ? E.inertia[(size_t)sc * nb + body] : E.mass[(size_t)sc * nb + body];
+      const T dpj = E.mode == 0 ? dx[j] : T(0);                     // dp = dx (:52); post-stabilisation has p = 0
+      if (a.dfext) a.dfext[(size_t)sc * n + j] = E.dt * dpj;
+      if (a.dv) {
+        T acc = md * dpj;
+        const int cnt = S.clcnt()[j];
+        for (int l = 0; l < cnt; ++l) {                             // the contacts that touch this dof
+          const int cp = S.clist()[l * n + j], c = cp >> 3, pslot = cp & 7;
+          const T hs_ = E.mode == 0 ? E.rest[(size_t)sc * nc + c] : (T(1) - E.rest[(size_t)sc * nc + c]);
+          acc += -dlam[c] * hs_ * S.Gd()[(size_t)pslot * P.pcap + c];      // dh_c d(h_c)/dv_j, Jc row = slot-0 rows of Gd
+        }
+        a.dv[(size_t)sc * n + j] = acc;
+      }
+      const T dqjj = dx[j] * zh_[j];                                // dQ_jj = 1/2 (dx_j z_j + z_j dx_j)  (:61)
+      if (comp == 0 && a.dinertia) a.dinertia[(size_t)sc * nb + body] = dqjj + dpj * v[j];
+    }
+    __syncthreads();
+    for (int body = tid; body < nb; body += NT) {
+      if (!a.dmass) break;
+      T acc = 0;
+      for (int comp = 1; comp < 3; ++comp) {
+        const int j = 3 * body + comp;
+        acc += dx[j] * zh_[j] + (E.mode == 0 ? dx[j] : T(0)) * v[j];
+      }
+      a.dmass[(size_t)sc * nb + body] = acc;
+    }
+    if (a.db && e > 0) for (int i = tid; i < e; i += NT) a.db[(size_t)sc * e + i] = -dnu[i];
+    if (a.dA && e > 0) {
+      T* o = a.dA + (size_t)sc * e * n;
+      for (int i = 0; i < e; ++i)
+        for (int j = tid; j < n; j += NT) o[(size_t)i * n + j] = dnu[i] * S.x()[j] + S.y()[i] * dx[j];
+    }
+    if (tid == 0 && a.done) a.done[sc] = 1;
+    __syncthreads();
+    pf.lap(CPH_GRADS);
+    return;
+  }
   if (a.dp) for (int i = tid; i < n; i += NT) a.dp[(size_t)sc * n + i] = dx[i];                       // :52
   if (a.dh) for (int i = tid; i < m; i += NT) a.dh[(size_t)sc * m + i] = -dlam[i];                    // :55
   if (a.db && e > 0) for (int i = tid; i < e; i += NT) a.db[(size_t)sc * e + i] = -dnu[i];            // :58
@@ -1178,9 +1392,10 @@ __global__ void __launch_bounds__(NT, (NS <= 6) ? 2 : 1) cond_backward_kernel(co
     __syncthreads();
     pf.start();
     Struct st;
-    const bool ok = build_structure<T>(P, S, st, a.Q + (size_t)sc * n * n, a.G + (size_t)sc * m * n,
-                                       e > 0 ? a.A + (size_t)sc * e * n : nullptr, a.F + (size_t)sc * m * m,
-                                       &singular_s);
+    const bool ok = a.soa.mass
+        ? build_structure_soa<T>(P, S, st, a.soa, sc, e > 0 ? a.A + (size_t)sc * e * n : nullptr, &singular_s)
+        : build_structure<T>(P, S, st, a.Q + (size_t)sc * n * n, a.G + (size_t)sc * m * n,
+                             e > 0 ? a.A + (size_t)sc * e * n : nullptr, a.F + (size_t)sc * m * m, &singular_s);
     __syncthreads();
     pf.lap(CPH_STRUCT);
     if (!ok) {

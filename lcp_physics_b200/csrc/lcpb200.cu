@@ -64,6 +64,7 @@ struct lcpb200_handle_s {
   size_t ws_bytes = 0;
   int ws_ctas = 0;
   DevBuf d_flag[NSLOT];    // per-scene "gradients already written" flags of the backward pass
+  DevBuf d_ph;             // engine path: p and h of every scene ([B,n] + [B,m])
   // host-buffer pipeline state
   cudaStream_t streams[NSLOT] = {nullptr, nullptr};
   DevBuf d_in[7], d_out[6], d_bwd[16];
@@ -266,6 +267,7 @@ extern "C" int lcpb200_destroy(lcpb200_handle_t h) {
   for (auto& b : h->d_out) b.release();
   for (auto& b : h->d_bwd) b.release();
   for (auto& b : h->d_flag) b.release();
+  h->d_ph.release();
   h->d_R.release();
   delete h;
   return 0;
@@ -310,6 +312,7 @@ static int launch_forward(lcpb200_handle_s* h, int slot, int B, const void* Q, c
     c.zhat = (T*)zhat; c.nu = (T*)nu; c.lam = (T*)lam; c.slack = (T*)slack; c.resid = (T*)resid;
     c.status = status; c.iters = iters;
     c.eps = (T)eps; c.not_improved_lim = not_improved_lim; c.max_iter = max_iter;
+    memset(&c.soa, 0, sizeof(c.soa));
     c.prof = h->cprof ? h->cprof + (size_t)slot * h->cond_grid * cnd::CPH_COUNT : nullptr;
     const int cgrid = std::min(B, h->cond_grid);
 #define CALL_FWD(NSV) cnd::launch_cond_forward_t<T, NSV>(c, cgrid, st)
@@ -367,6 +370,8 @@ static int launch_backward(lcpb200_handle_s* h, int slot, int B, const void* Q, 
     c.done = cond_first ? flagbuf : nullptr;
     c.only = cond_first ? nullptr : flagbuf;
     c.flags = flags;
+    memset(&c.soa, 0, sizeof(c.soa));
+    c.dmass = c.dinertia = c.dv = c.dfext = c.dnormal = c.dp1 = c.dp2 = c.dmu = c.drest = nullptr;
     c.prof = h->cprof ? h->cprof + (size_t)slot * h->cond_grid * cnd::CPH_COUNT : nullptr;
   }
   const int cgrid = std::min(B, std::max(h->cond_grid, 1));
@@ -633,6 +638,143 @@ extern "C" int lcpb200_backward_host(lcpb200_handle_t h, int B, const void* Q, c
   }
   for (auto& s : h->streams) CK(cudaStreamSynchronize(s));
   return 0;
+}
+
+
+// ------------------------------------------------------------------ fused engine entry points
+// Contact list in, velocities out: the condensed kernels take their structure straight from the
+// structure-of-arrays the engine holds; no dense Q / G / F is written to or read from HBM, and the
+// backward returns the gradients w.r.t. the contact list (the chain rule through the assembly is
+// applied to the factored gradients inside the kernel).
+template <typename T>
+static void fill_soa(cnd::EngineSoA<T>& s, lcpb200_handle_s* h, int B, int nb, int nc, int mode, double dt,
+                     const void* mass, const void* inertia, const void* v, const void* fext, const void* normal,
+                     const void* p1, const void* p2, const int32_t* b1, const int32_t* b2, const void* mu,
+                     const void* rest) {
+  s.mass = (const T*)mass; s.inertia = (const T*)inertia; s.v = (const T*)v; s.fext = (const T*)fext;
+  s.normal = (const T*)normal; s.p1 = (const T*)p1; s.p2 = (const T*)p2; s.mu = (const T*)mu; s.rest = (const T*)rest;
+  s.b1 = b1; s.b2 = b2; s.nb = nb; s.nc = nc; s.mode = mode; s.dt = (T)dt;
+  s.p_s = (T*)h->d_ph.p;
+  s.h_s = s.p_s + (size_t)B * h->n;
+}
+
+static int check_engine(lcpb200_handle_t h, int B, int nb, int nc, int mode) {
+  if (!h) return fail("null handle");
+  if (B < 0 || nb <= 0 || nc <= 0) return fail("need B >= 0, nb > 0, nc > 0");
+  if (mode != 0 && mode != 1) return fail("mode must be 0 (solve_dynamics) or 1 (post_stabilization)");
+  if (!h->cplan.ok) return fail("engine entry points need the condensed-KKT plan (n + e <= 128); use lcpb200_assemble + lcpb200_forward");
+  if (h->n != 3 * nb || h->m != (mode == 0 ? 4 : 1) * nc)
+    return fail("handle was created for other sizes: need n = 3 nb and m = 4 nc (mode 0) or nc (mode 1)");
+  return 0;
+}
+
+template <typename T>
+static int engine_forward_t(lcpb200_handle_s* h, int B, int nb, int nc, int mode, double dt, const void* mass,
+                            const void* inertia, const void* v, const void* fext, const void* normal, const void* p1,
+                            const void* p2, const int32_t* b1, const int32_t* b2, const void* mu, const void* rest,
+                            const void* A, const void* b, double eps, int not_improved_lim, int max_iter, void* zhat,
+                            void* nu, void* lam, void* slack, int32_t* status, int32_t* iters, void* resid,
+                            cudaStream_t st) {
+  CK(h->d_ph.ensure(sizeof(T) * (size_t)B * (h->n + h->m)));
+  cnd::CFwdArgs<T> c;
+  c.P = h->cplan;
+  c.B = B;
+  c.Q = nullptr; c.G = nullptr; c.F = nullptr;
+  c.A = (const T*)A; c.b = (const T*)b;
+  fill_soa<T>(c.soa, h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, b1, b2, mu, rest);
+  c.p = c.soa.p_s; c.h = c.soa.h_s;
+  c.zhat = (T*)zhat; c.nu = (T*)nu; c.lam = (T*)lam; c.slack = (T*)slack; c.resid = (T*)resid;
+  c.status = status; c.iters = iters;
+  c.eps = (T)eps; c.not_improved_lim = not_improved_lim; c.max_iter = max_iter;
+  c.prof = h->cprof;
+  const int cgrid = std::min(B, h->cond_grid);
+#define CALL_FWD(NSV) cnd::launch_cond_forward_t<T, NSV>(c, cgrid, st)
+  const cudaError_t ce = LCPB200_NS_DISPATCH(h->cplan.NS, CALL_FWD);
+#undef CALL_FWD
+  CK(ce);
+  return 0;
+}
+
+extern "C" int lcpb200_engine_forward(lcpb200_handle_t h, int B, int nb, int nc, int mode, double dt,
+                                      const void* mass, const void* inertia, const void* v, const void* fext,
+                                      const void* normal, const void* p1, const void* p2, const int32_t* body1,
+                                      const int32_t* body2, const void* mu, const void* restitution, const void* A,
+                                      const void* b, double eps, int not_improved_lim, int max_iter, void* zhat,
+                                      void* nu, void* lam, void* slack, int32_t* status, int32_t* iters, void* resid,
+                                      void* stream) {
+  if (int rc = check_engine(h, B, nb, nc, mode)) return rc;
+  if (!mass || !inertia || !v || !normal || !p1 || !p2 || !body1 || !body2 || !restitution) return fail("engine_forward: NULL input");
+  if (mode == 0 && (!fext || !mu)) return fail("engine_forward: fext and mu are needed for mode 0");
+  if (h->e > 0 && (!A || !b || !nu)) return fail("handle was created with e > 0 but A, b or nu is NULL");
+  if (!zhat || !lam || !slack || !status || !iters) return fail("zhat, lam, slack, status, iters must be non-NULL");
+  if (B == 0) return 0;
+  DeviceGuard dg_;
+  CK(dg_.set(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  return h->dtype == LCPB200_F32
+             ? engine_forward_t<float>(h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, body1, body2, mu,
+                                       restitution, A, b, eps, not_improved_lim, max_iter, zhat, nu, lam, slack, status,
+                                       iters, resid, st)
+             : engine_forward_t<double>(h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, body1, body2, mu,
+                                        restitution, A, b, eps, not_improved_lim, max_iter, zhat, nu, lam, slack, status,
+                                        iters, resid, st);
+}
+
+template <typename T>
+static int engine_backward_t(lcpb200_handle_s* h, int B, int nb, int nc, int mode, double dt, const void* mass,
+                             const void* inertia, const void* v, const void* fext, const void* normal, const void* p1,
+                             const void* p2, const int32_t* b1, const int32_t* b2, const void* mu, const void* rest,
+                             const void* A, const void* zhat, const void* nu, const void* lam, const void* slack,
+                             const void* g, void* dmass, void* dinertia, void* dv, void* dfext, void* dnormal,
+                             void* dp1, void* dp2, void* dmu, void* drest, void* dA, void* db, unsigned flags,
+                             cudaStream_t st) {
+  CK(h->d_ph.ensure(sizeof(T) * (size_t)B * (h->n + h->m)));
+  cnd::CBwdArgs<T> c;
+  c.P = h->cplan;
+  c.B = B;
+  c.Q = nullptr; c.G = nullptr; c.F = nullptr; c.A = (const T*)A;
+  c.zhat = (const T*)zhat; c.nu = (const T*)nu; c.lam = (const T*)lam; c.slack = (const T*)slack; c.g = (const T*)g;
+  c.dQ = c.dp = c.dG = c.dh = c.dF = nullptr;
+  c.dA = (T*)dA; c.db = (T*)db;
+  c.done = nullptr; c.only = nullptr; c.flags = flags;
+  c.prof = h->cprof;
+  fill_soa<T>(c.soa, h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, b1, b2, mu, rest);
+  c.dmass = (T*)dmass; c.dinertia = (T*)dinertia; c.dv = (T*)dv; c.dfext = (T*)dfext; c.dnormal = (T*)dnormal;
+  c.dp1 = (T*)dp1; c.dp2 = (T*)dp2; c.dmu = (T*)dmu; c.drest = (T*)drest;
+  const int cgrid = std::min(B, h->cond_grid);
+#define CALL_BWD(NSV) cnd::launch_cond_backward_t<T, NSV>(c, cgrid, st)
+  const cudaError_t ce = LCPB200_NS_DISPATCH(h->cplan.NS, CALL_BWD);
+#undef CALL_BWD
+  CK(ce);
+  return 0;
+}
+
+extern "C" int lcpb200_engine_backward(lcpb200_handle_t h, int B, int nb, int nc, int mode, double dt,
+                                       const void* mass, const void* inertia, const void* v, const void* fext,
+                                       const void* normal, const void* p1, const void* p2, const int32_t* body1,
+                                       const int32_t* body2, const void* mu, const void* restitution, const void* A,
+                                       const void* zhat, const void* nu, const void* lam, const void* slack,
+                                       const void* dl_dzhat, void* dmass, void* dinertia, void* dv, void* dfext,
+                                       void* dnormal, void* dp1, void* dp2, void* dmu, void* drestitution, void* dA,
+                                       void* db, unsigned flags, void* stream) {
+  if (int rc = check_engine(h, B, nb, nc, mode)) return rc;
+  if (!mass || !inertia || !v || !normal || !p1 || !p2 || !body1 || !body2 || !restitution) return fail("engine_backward: NULL input");
+  if (mode == 0 && !mu) return fail("engine_backward: mu is needed for mode 0");
+  if (!zhat || !lam || !slack || !dl_dzhat) return fail("zhat, lam, slack, dl_dzhat must be non-NULL");
+  if (h->e > 0 && (!A || !nu)) return fail("A and nu must be non-NULL when e > 0");
+  if (flags != LCPB200_BWD_BUG_COMPATIBLE && flags != LCPB200_BWD_EXACT_ADJOINT)
+    return fail("flags must be LCPB200_BWD_BUG_COMPATIBLE or LCPB200_BWD_EXACT_ADJOINT");
+  if (B == 0) return 0;
+  DeviceGuard dg_;
+  CK(dg_.set(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  return h->dtype == LCPB200_F32
+             ? engine_backward_t<float>(h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, body1, body2, mu,
+                                        restitution, A, zhat, nu, lam, slack, dl_dzhat, dmass, dinertia, dv, dfext,
+                                        dnormal, dp1, dp2, dmu, drestitution, dA, db, flags, st)
+             : engine_backward_t<double>(h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, body1, body2, mu,
+                                         restitution, A, zhat, nu, lam, slack, dl_dzhat, dmass, dinertia, dv, dfext,
+                                         dnormal, dp1, dp2, dmu, drestitution, dA, db, flags, st);
 }
 
 // ------------------------------------------------------------------ assembly

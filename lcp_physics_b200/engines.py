@@ -93,10 +93,78 @@ def assemble_contacts(mass, inertia, v, fext, normal, p1, p2, mu, rest, body1, b
     return _AssembleFn.apply(mass, inertia, v, fext, normal, p1, p2, mu, rest, body1, body2, dt)
 
 
+class _EngineSolveFn(torch.autograd.Function):
+    """Fused path (lcpb200_engine_forward / _backward): contact structure-of-arrays in, LCP solution out.
+    No dense Q / G / F exists anywhere; the backward returns gradients w.r.t. the contact list.
+    mode 0 = solve_dynamics' LCP (engines.py:50-76), mode 1 = post_stabilization's (engines.py:80-116)."""
+
+    @staticmethod
+    def forward(ctx, mass, inertia, v, fext, normal, p1, p2, mu, rest, A, b, body1, body2, dt, mode, max_iter, exact):
+        lib = _lib.load()
+        B, nb = mass.shape
+        nc = normal.shape[1]
+        n, m = 3 * nb, (4 if mode == 0 else 1) * nc
+        e = A.shape[1] if (A is not None and A.dim() > 1) else 0
+        dt_, dev = mass.dtype, mass.device
+        ins = [t.contiguous() for t in (mass, inertia, v, fext, normal, p1, p2)]
+        mu_c, rest_c = mu.contiguous(), rest.contiguous()
+        A_c = A.contiguous() if e > 0 else None
+        b_c = b.contiguous() if e > 0 else None
+        hd = _lib.get_handle(dt_, n, m, e, dev.index, torch.cuda.current_stream(dev).cuda_stream)
+        new = lambda *s, d=dt_: torch.empty(*s, dtype=d, device=dev)
+        zhat, lam, slack = new(B, n), new(B, m), new(B, m)
+        nu = new(B, e) if e > 0 else None
+        status, iters, resid = new(B, d=torch.int32), new(B, d=torch.int32), new(B)
+        with torch.cuda.device(dev):
+            _lib.check(lib.lcpb200_engine_forward(
+                hd.raw, B, nb, nc, int(mode), float(dt), *[_lib.ptr(t) for t in ins], _lib.ptr(body1), _lib.ptr(body2),
+                _lib.ptr(mu_c), _lib.ptr(rest_c), _lib.ptr(A_c), _lib.ptr(b_c), 1e-12, 3, int(max_iter),
+                *[_lib.ptr(t) for t in (zhat, nu, lam, slack, status, iters, resid)], _stream_ptr(dev)))
+        ctx.save_for_backward(*ins, mu_c, rest_c, A_c, body1, body2, zhat, nu, lam, slack)
+        ctx.meta = (float(dt), int(mode), bool(exact), B, nb, nc, e)
+        ctx.mark_non_differentiable(status)
+        return zhat, status
+
+    @staticmethod
+    def backward(ctx, dzhat, _dstatus):
+        lib = _lib.load()
+        (mass, inertia, v, fext, normal, p1, p2, mu, rest, A, body1, body2, zhat, nu, lam, slack) = ctx.saved_tensors
+        dt, mode, exact, B, nb, nc, e = ctx.meta
+        dev = mass.device
+        z = torch.zeros_like
+        outs = [z(mass), z(inertia), z(v), z(fext), z(normal), z(p1), z(p2), z(mu), z(rest)]
+        dA = z(A) if e > 0 else None
+        db = torch.zeros(B, e, dtype=mass.dtype, device=dev) if e > 0 else None
+        hd = _lib.get_handle(mass.dtype, 3 * nb, (4 if mode == 0 else 1) * nc, e, dev.index,
+                             torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            _lib.check(lib.lcpb200_engine_backward(
+                hd.raw, B, nb, nc, mode, dt, *[_lib.ptr(t) for t in (mass, inertia, v, fext, normal, p1, p2)],
+                _lib.ptr(body1), _lib.ptr(body2), _lib.ptr(mu), _lib.ptr(rest), _lib.ptr(A),
+                *[_lib.ptr(t) for t in (zhat, nu, lam, slack, dzhat.contiguous())],
+                *[_lib.ptr(t) for t in outs], _lib.ptr(dA), _lib.ptr(db), 1 if exact else 0, _stream_ptr(dev)))
+        return (*outs, dA, db, None, None, None, None, None, None)
+
+
+def engine_solve(mass, inertia, v, fext, normal, p1, p2, mu, rest, body1, body2, dt, A=None, b=None, mode=0,
+                 max_iter=10, exact_adjoint=False):
+    """Batched, differentiable LCP of the engine straight from the contact list (CUDA tensors):
+    mass/inertia [B,nb], v/fext [B,3nb], normal/p1/p2 [B,nc,2], mu/rest [B,nc], body1/body2 [nc] int32,
+    optional equality rows A [B,e,3nb], b [B,e]. Returns (zhat [B,3nb], status [B]); status == -100 marks a
+    scene whose topology the fused kernel does not take (use assemble_contacts + LCPFunction for it).
+    solve_dynamics: new_v = -zhat (engines.py:76); post_stabilization: dp = -zhat (engines.py:116)."""
+    _lib.require_cuda()
+    return _EngineSolveFn.apply(mass, inertia, v, fext, normal, p1, p2, mu, rest, A, b, body1, body2, dt, mode,
+                                max_iter, exact_adjoint)
+
+
 class B200PdipmEngine(Engine):
     """Engine that solves the contact LCP with the B200 PDIPM kernels (mirror of engines.py:17-116)."""
 
-    def __init__(self, max_iter=10):
+    def __init__(self, max_iter=10, fused=True):
+        # fused: contact list -> solution in one kernel (lcpb200_engine_forward); False (or an unsupported
+        # topology / size) assembles the dense LCP on the GPU and calls LCPFunction, like the reference
+        self.fused = fused
         self.lcp_solver = LCPFunction
         self.cached_inverse = None
         self.max_iter = max_iter
@@ -144,6 +212,33 @@ class B200PdipmEngine(Engine):
         return assemble_contacts(mass.to(dev), inertia.to(dev), v.unsqueeze(0).to(dev), fext.unsqueeze(0).to(dev),
                                  normal, p1, p2, mu, rest, b1, b2, dt), n
 
+    def _fused(self, world, dt, fext, Je, ge, dev, mode, max_iter):
+        """One lcpb200_engine_forward call for this world (batch of one); None when the fused kernel cannot
+        take it (n + neq > 128, non-diagonal M, vec_len != 3, unsupported topology)."""
+        M = world.M()
+        Md = torch.diagonal(M)
+        neq = Je.size(0) if Je.ndimension() > 0 else 0
+        if world.vec_len != 3 or M.size(0) + neq > 128 or len(world.contacts) * 4 > 1024:
+            return None
+        if bool((M - torch.diag(Md)).abs().max() != 0):
+            return None
+        Mb = Md.reshape(-1, 3)
+        normal, p1, p2, b1, b2, mu, rest = self._contact_soa(world, dev)
+        v = world.get_v()
+        if neq > 0:
+            A = Je.unsqueeze(0).to(dev)
+            b = (ge.unsqueeze(0).to(dev) if ge is not None else A.new_zeros(1, neq))
+        else:
+            A = b = None
+        x, status = engine_solve(Mb[:, 1].unsqueeze(0).to(dev), Mb[:, 0].unsqueeze(0).to(dev), v.unsqueeze(0).to(dev),
+                                 fext.unsqueeze(0).to(dev), normal, p1, p2, mu, rest, b1, b2, dt, A=A, b=b, mode=mode,
+                                 max_iter=max_iter)
+        st = int(status[0])
+        if st == _lib.STATUS_SINGULAR_Q:
+            from .lcp import SINGULAR_Q_MSG
+            raise RuntimeError(SINGULAR_Q_MSG)
+        return None if st == -100 else x
+
     # ------------------------------------------------------------------ engines.py:26-78
     def solve_dynamics(self, world, dt):
         t = world.t
@@ -170,6 +265,10 @@ class B200PdipmEngine(Engine):
             x = torch.matmul(inv, u)
             return x[:world.vec_len * len(world.bodies)]
         dev = self._device()
+        if self.fused and self.lcp_solver is LCPFunction:
+            x = self._fused(world, dt, f, Je, None, dev, mode=0, max_iter=self.max_iter)
+            if x is not None:
+                return (-x).squeeze(0).to(v0.device)                  # engines.py:76
         (Q, p, G, h, F), n = self._assemble(world, dt, f, dev)
         if neq > 0:
             A = Je.unsqueeze(0).to(dev)
@@ -199,6 +298,10 @@ class B200PdipmEngine(Engine):
             return -x[:M.size(0)]
         dev = self._device()
         fzero = v.new_zeros(v.shape)
+        if self.fused and self.lcp_solver is LCPFunction:
+            x = self._fused(world, 0.0, fzero, Je, ge, dev, mode=1, max_iter=10)      # engines.py:114: default max_iter
+            if x is not None:
+                return (-x).to(v.device)
         (Q, _p, G, _h, _F), n = self._assemble(world, 0.0, fzero, dev)
         nc = len(world.contacts)
         Jc = G[:, :nc, :]

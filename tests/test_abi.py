@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), n
     assert set(names) == set(_lib.EXPORTS)
     lib.lcpb200_version.restype = ctypes.c_int
-    assert lib.lcpb200_version() == 100
+    assert lib.lcpb200_version() == 200
 
 
 def test_no_cpu_fallback():

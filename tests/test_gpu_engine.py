@@ -10,15 +10,17 @@ from tests.helpers import ReplayWorld, load_world_records, rel_err
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("name", ["world_pile", "world_chain"])
-def test_engine_replays_reference_world(name):
+def test_engine_replays_reference_world(name, fused):
+    """fused=True: lcpb200_engine_forward (contact list -> solution, nothing dense); False: GPU assembly + LCPFunction."""
     from lcp_physics_b200.engines import B200PdipmEngine
     recs = load_world_records(name)
     assert len(recs) >= 20
     worst = 0.0
     for rec in recs:
         world = ReplayWorld(rec)
-        eng = B200PdipmEngine()
+        eng = B200PdipmEngine(fused=fused)
         if str(rec["kind"]) == "solve_dynamics":
             out = eng.solve_dynamics(world, float(rec["dt"]))
         else:
@@ -64,3 +66,69 @@ def test_assemble_kernel_matches_torch_and_is_differentiable():
     for k in names:
         assert rel_err(leaves[k].grad.cpu().reshape(B, -1), cl[k].grad.reshape(B, -1)).max() < 1e-10, k
     assert rel_err(fx.grad.cpu(), fx2.grad).max() < 1e-12
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("e", [0, 3])
+def test_fused_engine_solve_matches_assemble_plus_lcpfunction(dtype, e):
+    """engine_solve (one kernel from the contact list) against assemble_contacts + LCPFunction (dense tensors in
+    HBM) on a batch: same solution, same gradients w.r.t. every contact-list input."""
+    from lcp_physics_b200 import LCPFunction
+    from lcp_physics_b200.engines import assemble_contacts, engine_solve
+    from lcp_physics_b200.scenes import make_contact_soa
+    B, nb, nc, dt = 7, 8, 12, 1.0 / 30
+    soa = make_contact_soa(B, nb, nc, seed=6)
+    fext = torch.zeros(B, 3 * nb, dtype=torch.float64)
+    fext[:, 2::3] = 10.0 * soa["mass"]
+    names = ["mass", "inertia", "v", "normal", "p1", "p2", "mu", "restitution"]
+    b1, b2 = soa["body1"].cuda(), soa["body2"].cuda()
+    gen = torch.Generator().manual_seed(2)
+    w = torch.randn(B, 3 * nb, generator=gen, dtype=torch.float64).to(dtype).cuda()
+    if e:
+        A0 = torch.zeros(B, e, 3 * nb, dtype=torch.float64)
+        A0[:, torch.arange(e), torch.arange(e)] = 1
+        A0 = A0.to(dtype).cuda()
+        b0 = torch.zeros(B, e, dtype=dtype).cuda()
+    grads = []
+    for fused in (True, False):
+        lv = {k: soa[k].to(dtype).cuda().requires_grad_(True) for k in names}
+        fx = fext.to(dtype).cuda().requires_grad_(True)
+        args = (lv["mass"], lv["inertia"], lv["v"], fx, lv["normal"], lv["p1"], lv["p2"], lv["mu"], lv["restitution"])
+        if fused:
+            z, status = engine_solve(*args, b1, b2, dt, A=A0 if e else None, b=b0 if e else None, max_iter=5)
+            assert (status >= 0).all()
+        else:
+            Q, p, G, h, F = assemble_contacts(*args, b1, b2, dt)
+            A = A0 if e else torch.tensor([], dtype=dtype, device="cuda")
+            bb = b0 if e else torch.tensor([], dtype=dtype, device="cuda")
+            z = LCPFunction(max_iter=5)(Q, p, G, h, A, bb, F)
+        (z * w).sum().backward()
+        grads.append((z.detach().cpu(), {k: lv[k].grad.cpu() for k in names}, fx.grad.cpu()))
+    (zf, gf, ff), (zd, gd, fd) = grads
+    # (5 iterations: away from the round-off floor, where the fp64 condensed and dual backward kernels agree)
+    ftol, gtol = (1e-9, 1e-5) if dtype == torch.float64 else (1e-3, 5e-3)
+    assert rel_err(zf, zd).max() < ftol
+    for k in names:
+        assert rel_err(gf[k].reshape(B, -1), gd[k].reshape(B, -1)).max() < gtol, k
+    assert rel_err(ff, fd).max() < gtol
+
+
+def test_fused_engine_solve_full_size_cfg3_matches_dense_path():
+    """The fused entry point at the BASELINE size (4096 scenes x 64 contacts, fp32) against the dense API on the
+    same scenes: the two paths build the same structure, so the results agree to fp32 round-off on most scenes."""
+    from lcp_physics_b200 import solve_forward
+    from lcp_physics_b200.engines import engine_solve
+    from lcp_physics_b200.scenes import assemble_dense, make_contact_soa
+    B, nb, nc, dt = 4096, 32, 64, 1.0 / 30
+    soa = make_contact_soa(B, nb, nc, seed=7)
+    dense = [t.float().cuda() for t in assemble_dense(soa, fd=2, e=0, dt=dt, gravity=10.0)]
+    fext = torch.zeros(B, 3 * nb, dtype=torch.float64)
+    fext[:, 2::3] = 10.0 * soa["mass"]
+    f32 = lambda t: t.float().cuda()
+    z, status = engine_solve(f32(soa["mass"]), f32(soa["inertia"]), f32(soa["v"]), f32(fext), f32(soa["normal"]),
+                             f32(soa["p1"]), f32(soa["p2"]), f32(soa["mu"]), f32(soa["restitution"]),
+                             soa["body1"].cuda(), soa["body2"].cuda(), dt, max_iter=10)
+    assert (status >= 0).all() and torch.isfinite(z).all()
+    zd = solve_forward(*dense, max_iter=10)[0]
+    err = rel_err(z.cpu(), zd.cpu())
+    assert (err < 1e-3).float().mean() > 0.97 and err.median() < 1e-5, (err.median(), err.max())
