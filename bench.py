@@ -226,6 +226,58 @@ def parity_sample(inp_host, g_host, fo_dev, bo_dev, n_sample, dtype, max_iter, w
 TOL = {torch.float32: 1e-3, torch.float64: 1e-6}
 
 
+def engine_path_leg(B, rank, dev, g, steps, warmup, barrier, world):
+    """cfg 3's scenes (same seed, hence the same LCPs) solved from their contact structure-of-arrays:
+    forward + backward (9 gradients w.r.t. the contact list). `value`: SoA resident in HBM; `e2e`: SoA in pinned
+    host memory, H2D + D2H of every result inside the timed region (a few KB per scene instead of 0.8 MB)."""
+    import torch.distributed as dist
+    from lcp_physics_b200.engines import engine_solve
+    from lcp_physics_b200.scenes import make_contact_soa
+    soa = make_contact_soa(B, NB, NC, seed=1000 + rank, dtype=torch.float64)
+    fext = torch.zeros(B, 3 * NB, dtype=torch.float64)
+    fext[:, 2::3] = 10.0 * soa["mass"]
+    names = ["mass", "inertia", "v", "fext", "normal", "p1", "p2", "mu", "restitution"]
+    host = {k: (fext if k == "fext" else soa[k]).float().pin_memory() for k in names}
+    b1, b2 = soa["body1"].to(dev), soa["body2"].to(dev)
+    devt = {k: host[k].to(dev) for k in names}
+
+    def step(src, to_host):
+        lv = [src[k].to(dev, non_blocking=True).requires_grad_(True) for k in names]
+        z, status = engine_solve(*lv, b1, b2, 1.0 / 30, max_iter=MAX_ITER)
+        (z * g).sum().backward()
+        if to_host:
+            return [z.detach().cpu()] + [t.grad.cpu() for t in lv]
+        return None
+
+    for _ in range(max(1, warmup)):
+        step(devt, False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step(devt, False)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    step(host, True)
+    barrier()
+    n_e2e = max(1, min(steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        step(host, True)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_s = t.tolist()
+    per_scene = sum(host[k][0].numel() for k in names) * 4
+    return {"api": "lcp_physics_b200.engines.engine_solve (lcpb200_engine_forward/_backward), fwd+bwd, same scenes as the headline",
+            "value": world * B * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+            "e2e": {"value": world * B * n_e2e / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": per_scene * B, "d2h_bytes_per_step": (per_scene + 3 * NB * 4) * B}}
+
+
 def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     from lcp_physics_b200 import _lib, solve_forward, solve_backward
@@ -344,6 +396,12 @@ def run_b200(args, rank, world, local_rank):
     h2d = in_bytes + (n_dof * w * B if with_bwd else 0)     # the 7 inputs once (kept on the device) + dl_dzhat
     d2h = ((n_dof + 2 * m_ineq + 1) * w + 8) * B + (in_bytes if with_bwd else 0)   # zhat, lam, slack, resid, status, iters (+ the 7 gradients)
 
+    # ---- the same scenes through the fused engine entry points (contact list in, gradients w.r.t. the contact
+    # list out: lcpb200_engine_forward / _backward) -- what B200PdipmEngine calls; reported next to the headline
+    eng = None
+    if not cfg2:
+        eng = engine_path_leg(B, rank, dev, g, args.steps, args.warmup, barrier, world)
+
     if rank != 0:
         return
     alg = algorithmic(n_dof, m_ineq, neq, w, iters_mean)
@@ -394,6 +452,8 @@ def run_b200(args, rank, world, local_rank):
                                       "definition": "every input read once, every output written once / forward time"}},
         "clocks": clocks,
     }
+    if not cfg2:
+        line["engine_path"] = eng
     if world == 1 and not args.no_cpu_baseline:
         ncores = use_all_host_threads()
         par, val, dt = parity_sample(inp_host, g_host, fo, bo, args.cpu_sample, dtype, MAX_ITER, with_bwd)

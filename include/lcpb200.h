@@ -177,12 +177,17 @@ int lcpb200_assemble_backward(int dtype, int B, int nb, int nc, double dt,
  * n = 3 nb, m = 4 nc (mode 0) or nc (mode 1), and n + e <= 128 (the condensed-KKT kernels). A scene whose
  * contact topology the kernel cannot take (a contact of a body with itself, > 16 contact rows per degree of
  * freedom) gets status -100 and no result: assemble it with lcpb200_assemble and call lcpb200_forward.
+ * contact_count == NULL: every scene has the nc contacts body1[nc], body2[nc] (one topology for the batch).
+ * contact_count[B] != NULL (batched worlds): scene s uses its first contact_count[s] <= nc contacts, body1 /
+ * body2 are [B,nc] and all per-contact arrays are strided by nc; a scene with 0 contacts gets the
+ * equality-constrained solve of engines.py:35-49; lam / slack rows of scene s are laid out for ITS count
+ * (normal rows [0,c), friction [c,3c), gamma [3c,4c)), the arrays keep the stride m.
  * lcpb200_engine_backward: the chain rule through the assembly applied to the factored gradients of
  * lcp.py:52-63 (dG = dlam (x) zhat + lam (x) dx, ...): gradients w.r.t. the contact list, any may be NULL. */
 int lcpb200_engine_forward(lcpb200_handle_t h, int B, int nb, int nc, int mode, double dt,
                            const void* mass, const void* inertia, const void* v, const void* fext,
                            const void* normal, const void* p1, const void* p2,
-                           const int32_t* body1, const int32_t* body2,
+                           const int32_t* body1, const int32_t* body2, const int32_t* contact_count,
                            const void* mu, const void* restitution, const void* A, const void* b,
                            double eps, int not_improved_lim, int max_iter,
                            void* zhat, void* nu, void* lam, void* slack,
@@ -190,7 +195,7 @@ int lcpb200_engine_forward(lcpb200_handle_t h, int B, int nb, int nc, int mode, 
 int lcpb200_engine_backward(lcpb200_handle_t h, int B, int nb, int nc, int mode, double dt,
                             const void* mass, const void* inertia, const void* v, const void* fext,
                             const void* normal, const void* p1, const void* p2,
-                            const int32_t* body1, const int32_t* body2,
+                            const int32_t* body1, const int32_t* body2, const int32_t* contact_count,
                             const void* mu, const void* restitution, const void* A,
                             const void* zhat, const void* nu, const void* lam, const void* slack,
                             const void* dl_dzhat,

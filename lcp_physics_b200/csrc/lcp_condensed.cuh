@@ -128,6 +128,7 @@ struct CSmem {
 struct Struct {
   int ncomp, cs;              // components, rows per component (uniform stride; short ones padded)
   int sh;                     // log2 of the smallest power of two >= ncomp: (r, c) = (t >> sh, t & mask) without divisions
+  int m;                      // inequality rows of THIS scene (== P.m, or 4 nc_s / nc_s on the engine path with per-scene contact counts)
 };
 
 // optional per-phase SM cycle counters (thread 0 of every CTA; lcpb200_profile)
@@ -315,7 +316,7 @@ __device__ __noinline__ bool build_structure(const CPlan& P, CSmem<T>& S, Struct
   __syncthreads();
   const int cs = flags[3];
   if (cs > CSMAX || ncomp * cs > pcap || ncomp * cs * cs > P.wcap || ncomp > 8191) return false;
-  st.ncomp = ncomp; st.cs = cs;
+  st.ncomp = ncomp; st.cs = cs; st.m = m;
   st.sh = 0;
   while ((1 << st.sh) < ncomp) ++st.sh;
   const int npos = ncomp * cs;
@@ -396,7 +397,8 @@ struct EngineSoA {
   const T *mass, *inertia, *v, *fext;         // [B,nb] [B,nb] [B,n] [B,n];  mass == nullptr: dense inputs
   const T *normal, *p1, *p2;                  // [B,nc,2]
   const T *mu, *rest;                         // [B,nc]
-  const int32_t *b1, *b2;                     // [nc] contact topology, shared by the batch
+  const int32_t *b1, *b2;                     // [nc] contact topology, shared by the batch ([B,nc] when nc_s != nullptr)
+  const int32_t* nc_s;                        // nullptr, or [B]: contacts of each scene (<= nc; arrays are strided by nc)
   int nb, nc;
   int mode;                                   // 0: solve_dynamics (engines.py:50-76), 1: post_stabilization (engines.py:80-116)
   T dt;
@@ -414,20 +416,24 @@ __device__ __forceinline__ void contact_row(T p1x, T p1y, T p2x, T p2y, T dx, T 
 template <typename T>
 __device__ __noinline__ bool build_structure_soa(const CPlan& P, CSmem<T>& S, Struct& st, const EngineSoA<T>& e_,
                                                  int sc, const T* __restrict__ A, int* singular) {
-  const int n = P.n, m = P.m, e = P.e, tid = threadIdx.x, pcap = P.pcap;
-  const int nb = e_.nb, nc = e_.nc, cs = e_.mode == 0 ? 4 : 1;
+  const int n = P.n, e = P.e, tid = threadIdx.x, pcap = P.pcap;
+  const int nb = e_.nb, ncs = e_.nc, cs = e_.mode == 0 ? 4 : 1;          // ncs: stride of the per-contact arrays
+  const int nc = e_.nc_s ? e_.nc_s[sc] : e_.nc;                          // contacts of this scene
+  const int m = cs * nc;
+  const int32_t* tb1 = e_.b1 + (e_.nc_s ? (size_t)sc * ncs : 0);
+  const int32_t* tb2 = e_.b2 + (e_.nc_s ? (size_t)sc * ncs : 0);
   char* sb = reinterpret_cast<char*>(S.K());
   unsigned short* cl_tmp = reinterpret_cast<unsigned short*>(sb);                      // [LMAX][n]
   int* cl_cnt = reinterpret_cast<int*>(sb + al16((size_t)LMAX * n * 2));               // [n]
-  if (n != 3 * nb || m != cs * nc || nc * cs > pcap || nc * cs * cs > P.wcap) return false;
+  if (n != 3 * nb || nc < 0 || nc > ncs || m > P.m || nc * cs > pcap || nc * cs * cs > P.wcap) return false;
   const T* mass = e_.mass + (size_t)sc * nb;
   const T* inertia = e_.inertia + (size_t)sc * nb;
   const T* v = e_.v + (size_t)sc * n;
-  const T* normal = e_.normal + (size_t)sc * nc * 2;
-  const T* p1 = e_.p1 + (size_t)sc * nc * 2;
-  const T* p2 = e_.p2 + (size_t)sc * nc * 2;
+  const T* normal = e_.normal + (size_t)sc * ncs * 2;
+  const T* p1 = e_.p1 + (size_t)sc * ncs * 2;
+  const T* p2 = e_.p2 + (size_t)sc * ncs * 2;
   T* ps = e_.p_s + (size_t)sc * n;
-  T* hs = e_.h_s + (size_t)sc * m;
+  T* hs = e_.h_s + (size_t)sc * P.m;
   int bad = 0;
   for (int j = tid; j < n; j += NT) {
     const int body = j / 3;
@@ -438,14 +444,14 @@ __device__ __noinline__ bool build_structure_soa(const CPlan& P, CSmem<T>& S, St
     cl_cnt[j] = 0;
   }
   for (int t = tid; t < e * n; t += NT) S.As()[t] = A[t];
-  st.ncomp = nc; st.cs = cs;
+  st.ncomp = nc; st.cs = cs; st.m = m;
   st.sh = 0;
   while ((1 << st.sh) < nc) ++st.sh;
   for (int t = tid; t < UC * pcap; t += NT) { S.Gd()[t] = T(0); S.ccols()[t] = 0; }
   for (int t = tid; t < nc * cs * cs; t += NT) S.Fd()[t] = T(0);
   __syncthreads();
   for (int c = tid; c < nc; c += NT) {
-    const int b1 = e_.b1[c], b2 = e_.b2[c];
+    const int b1 = tb1[c], b2 = tb2[c];
     if (b1 == b2 || b1 < 0 || b2 < 0 || b1 >= nb || b2 >= nb) { bad |= 1; continue; }
     const int lo = min(b1, b2), hi = max(b1, b2);
     const int o1 = b1 < b2 ? 0 : 3, o2 = 3 - o1;                   // slots of body1 / body2 in the sorted column list
@@ -461,7 +467,7 @@ __device__ __noinline__ bool build_structure_soa(const CPlan& P, CSmem<T>& S, St
     contact_row<T>(p1x, p1y, p2x, p2y, nx, ny, r1, r2);            // Jc row
     const T jv = r1[0] * v[3 * b1] + r1[1] * v[3 * b1 + 1] + r1[2] * v[3 * b1 + 2] +
                  r2[0] * v[3 * b2] + r2[1] * v[3 * b2 + 1] + r2[2] * v[3 * b2 + 2];
-    const T rc = e_.rest[(size_t)sc * nc + c];
+    const T rc = e_.rest[(size_t)sc * ncs + c];
 #pragma unroll
     for (int q = 0; q < 3; ++q) { S.Gd()[(size_t)(o1 + q) * pcap + c] = r1[q]; S.Gd()[(size_t)(o2 + q) * pcap + c] = r2[q]; }
     S.rows()[c] = (unsigned short)c;
@@ -481,7 +487,7 @@ __device__ __noinline__ bool build_structure_soa(const CPlan& P, CSmem<T>& S, St
       // F = [[0,0,0],[0,0,E],[mu,-E^T,0]]  (engines.py:69-73): rows/cols {c, f1, f2, gamma} of the component
       S.Fd()[(size_t)(1 * 4 + 3) * nc + c] = T(1);
       S.Fd()[(size_t)(2 * 4 + 3) * nc + c] = T(1);
-      S.Fd()[(size_t)(3 * 4 + 0) * nc + c] = e_.mu[(size_t)sc * nc + c];
+      S.Fd()[(size_t)(3 * 4 + 0) * nc + c] = e_.mu[(size_t)sc * ncs + c];
       S.Fd()[(size_t)(3 * 4 + 1) * nc + c] = T(-1);
       S.Fd()[(size_t)(3 * 4 + 2) * nc + c] = T(-1);
     } else {
@@ -1046,13 +1052,13 @@ template <typename T, int NS, int CS>
 __device__ __forceinline__ void forward_scene(const CFwdArgs<T>& a, CSmem<T>& S, const Struct& st, Prof& pf, int sc) {
   const int nc_ = st.ncomp;                       // positions are slot-major: pos(c, r) = r * ncomp + c
   const CPlan& P = a.P;
-  const int n = P.n, m = P.m, e = P.e, tid = threadIdx.x, pcap = P.pcap;
+  const int n = P.n, m = st.m, e = P.e, tid = threadIdx.x, pcap = P.pcap;      // m: this scene's rows (<= P.m, the stride)
   const T* p = a.p + (size_t)sc * n;
-  const T* h = a.h + (size_t)sc * m;
+  const T* h = a.h + (size_t)sc * P.m;
   const T* b = e > 0 ? a.b + (size_t)sc * e : nullptr;
   T* o_x = a.zhat + (size_t)sc * n;
-  T* o_z = a.lam + (size_t)sc * m;
-  T* o_s = a.slack + (size_t)sc * m;
+  T* o_z = a.lam + (size_t)sc * P.m;
+  T* o_s = a.slack + (size_t)sc * P.m;
   T* o_y = e > 0 ? a.nu + (size_t)sc * e : nullptr;
   const T NANV = nan("");
 
@@ -1063,6 +1069,14 @@ __device__ __forceinline__ void forward_scene(const CFwdArgs<T>& a, CSmem<T>& S,
   __syncthreads();
   factor_kkt<T, NS, CS>(P, S, st, pf);
   solve_kkt<T, CS, NS>(P, S, st, pf, S.rx(), S.rs2(), S.rz(), e > 0 ? S.ry() : nullptr, S.x(), S.s(), S.z(), S.y());
+  if (m == 0) {
+    // engine path, a scene without contacts: no complementarity, the equality-constrained solve above is the
+    // answer (engines.py:35-49 solves [[M, -Je^T], [Je, 0]] x = [M v + dt f; 0] directly in that case)
+    for (int i = tid; i < n; i += NT) o_x[i] = S.x()[i];
+    for (int i = tid; i < e; i += NT) o_y[i] = S.y()[i];
+    if (tid == 0) { a.status[sc] = 2; a.iters[sc] = 0; if (a.resid) a.resid[sc] = T(0); }
+    return;
+  }
   {   // shift s and z to >= 1 where the row minimum is <= 0       :65-75
     T mn[2] = {INFINITY, INFINITY};
     for (int i = tid; i < m; i += NT) { mn[0] = nan_min(mn[0], S.s()[i]); mn[1] = nan_min(mn[1], S.z()[i]); }
@@ -1227,17 +1241,26 @@ __global__ void __launch_bounds__(NT, (NS <= 6) ? 2 : 1) cond_forward_kernel(con
 template <typename T, int NS, int CS>
 __device__ __forceinline__ void backward_scene(const CBwdArgs<T>& a, CSmem<T>& S, const Struct& st, Prof& pf, int sc) {
   const CPlan& P = a.P;
-  const int n = P.n, m = P.m, e = P.e, tid = threadIdx.x;
+  const int n = P.n, m = st.m, e = P.e, tid = threadIdx.x;
   const T* zh = a.zhat + (size_t)sc * n;
-  const T* lam = a.lam + (size_t)sc * m;
-  const T* slk = a.slack + (size_t)sc * m;
+  const T* lam = a.lam + (size_t)sc * P.m;
+  const T* slk = a.slack + (size_t)sc * P.m;
   const T* nu = e > 0 ? a.nu + (size_t)sc * e : nullptr;
   for (int i = tid; i < n; i += NT) { S.x()[i] = zh[i]; S.rx()[i] = a.g[(size_t)sc * n + i]; }
-  for (int i = tid; i < m; i += NT) { S.z()[i] = lam[i]; S.s()[i] = slk[i]; S.d()[i] = lam[i] / slk[i]; S.rs2()[i] = T(0); }   // :44
+  for (int i = tid; i < m; i += NT) {
+    T d = lam[i] / slk[i];                                                              // :44
+    // fp64 only: at the round-off floor (lambda, s ~ 1e-16) d spans 1e+-16 and the condensed matrix
+    // K = Q + G^T (F + 1/d)^-1 G, which inherits the large entries, can no longer be factored (kappa u >= 1,
+    // exact zero pivots). Clamping d to [1e-10, 1e10] moves the KKT diagonal of rows that are converged
+    // to 1e-16 by < 1e-10 -- far below the 1e-4 at which the reference's own gradients are reproducible
+    // there (tests/test_oracle.py) -- and keeps kappa(K) u <= 1e-6.
+    if (sizeof(T) == 8) d = d > T(1e10) ? T(1e10) : (d < T(1e-10) ? T(1e-10) : d);
+    S.z()[i] = lam[i]; S.s()[i] = slk[i]; S.d()[i] = d; S.rs2()[i] = T(0);
+  }
   for (int i = tid; i < e; i += NT) S.y()[i] = nu[i];
   __syncthreads();
   const bool exact = (a.flags & 1u) != 0;
-  factor_kkt<T, NS, CS>(P, S, st, pf, exact);                                               // :46
+  factor_kkt<T, NS, CS>(P, S, st, pf, exact);                                               // :46  (m == 0: K = [[Q, A^T], [A, 0]])
   solve_kkt<T, CS, NS>(P, S, st, pf, S.rx(), S.rs2(), nullptr, nullptr, S.dx(), S.ds(), S.dz(), S.dy(), exact);   // :47-50
   const T* dx = S.dx(); const T* dlam = S.dz(); const T* dnu = S.dy();
   if (a.soa.mass) {
@@ -1245,14 +1268,24 @@ __device__ __forceinline__ void backward_scene(const CBwdArgs<T>& a, CSmem<T>& S
     // FACTORED gradients of lcp.py:52-63 -- dG = dlam (x) zhat + lam (x) dx, dF = -dlam (x) lam, dh = -dlam,
     // dQ = sym(dx (x) zhat), dp = dx -- evaluated only at the entries the assembly writes.
     const EngineSoA<T>& E = a.soa;
-    const int nc = E.nc, nb = E.nb;
+    const int nc = st.ncomp, nb = E.nb, ncs = E.nc;             // nc: this scene's contacts, ncs: array stride
+    const int32_t* tb1 = E.b1 + (E.nc_s ? (size_t)sc * ncs : 0);
+    const int32_t* tb2 = E.b2 + (E.nc_s ? (size_t)sc * ncs : 0);
     const T* v = E.v + (size_t)sc * n;
     const T* zh_ = S.x(); const T* lm = S.z();
-    for (int c = tid; c < nc; c += NT) {
-      const size_t ic = (size_t)sc * nc + c;
+    for (int c = tid; c < ncs; c += NT) {
+      const size_t ic = (size_t)sc * ncs + c;
+      if (c >= nc) {                                              // unused slots of a scene with fewer contacts
+        if (a.dnormal) { a.dnormal[ic * 2] = 0; a.dnormal[ic * 2 + 1] = 0; }
+        if (a.dp1) { a.dp1[ic * 2] = 0; a.dp1[ic * 2 + 1] = 0; }
+        if (a.dp2) { a.dp2[ic * 2] = 0; a.dp2[ic * 2 + 1] = 0; }
+        if (a.drest) a.drest[ic] = 0;
+        if (a.dmu) a.dmu[ic] = 0;
+        continue;
+      }
       const T nx = E.normal[ic * 2], ny = E.normal[ic * 2 + 1];
       const T p1x = E.p1[ic * 2], p1y = E.p1[ic * 2 + 1], p2x = E.p2[ic * 2], p2y = E.p2[ic * 2 + 1];
-      const int j1 = 3 * E.b1[c], j2 = 3 * E.b2[c];
+      const int j1 = 3 * tb1[c], j2 = 3 * tb2[c];
       const T rc = E.rest[ic];
       const T dhc = -dlam[c] * (E.mode == 0 ? T(1) : T(1));      // dh = -dlam  (:55)
       T gnx = 0, gny = 0, g1x = 0, g1y = 0, g2x = 0, g2y = 0, jcv = 0;
@@ -1297,7 +1330,7 @@ __device__ __forceinline__ void backward_scene(const CBwdArgs<T>& a, CSmem<T>& S
         const int cnt = S.clcnt()[j];
         for (int l = 0; l < cnt; ++l) {                             // the contacts that touch this dof
           const int cp = S.clist()[l * n + j], c = cp >> 3, pslot = cp & 7;
-          const T hs_ = E.mode == 0 ? E.rest[(size_t)sc * nc + c] : (T(1) - E.rest[(size_t)sc * nc + c]);
+          const T hs_ = E.mode == 0 ? E.rest[(size_t)sc * ncs + c] : (T(1) - E.rest[(size_t)sc * ncs + c]);
           acc += -dlam[c] * hs_ * S.Gd()[(size_t)pslot * P.pcap + c];      // dh_c d(h_c)/dv_j, Jc row = slot-0 rows of Gd
         }
         a.dv[(size_t)sc * n + j] = acc;

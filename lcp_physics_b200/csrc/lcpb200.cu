@@ -650,10 +650,10 @@ template <typename T>
 static void fill_soa(cnd::EngineSoA<T>& s, lcpb200_handle_s* h, int B, int nb, int nc, int mode, double dt,
                      const void* mass, const void* inertia, const void* v, const void* fext, const void* normal,
                      const void* p1, const void* p2, const int32_t* b1, const int32_t* b2, const void* mu,
-                     const void* rest) {
+                     const void* rest, const int32_t* nc_s = nullptr) {
   s.mass = (const T*)mass; s.inertia = (const T*)inertia; s.v = (const T*)v; s.fext = (const T*)fext;
   s.normal = (const T*)normal; s.p1 = (const T*)p1; s.p2 = (const T*)p2; s.mu = (const T*)mu; s.rest = (const T*)rest;
-  s.b1 = b1; s.b2 = b2; s.nb = nb; s.nc = nc; s.mode = mode; s.dt = (T)dt;
+  s.b1 = b1; s.b2 = b2; s.nc_s = nc_s; s.nb = nb; s.nc = nc; s.mode = mode; s.dt = (T)dt;
   s.p_s = (T*)h->d_ph.p;
   s.h_s = s.p_s + (size_t)B * h->n;
 }
@@ -671,8 +671,8 @@ static int check_engine(lcpb200_handle_t h, int B, int nb, int nc, int mode) {
 template <typename T>
 static int engine_forward_t(lcpb200_handle_s* h, int B, int nb, int nc, int mode, double dt, const void* mass,
                             const void* inertia, const void* v, const void* fext, const void* normal, const void* p1,
-                            const void* p2, const int32_t* b1, const int32_t* b2, const void* mu, const void* rest,
-                            const void* A, const void* b, double eps, int not_improved_lim, int max_iter, void* zhat,
+                            const void* p2, const int32_t* b1, const int32_t* b2, const int32_t* ncs, const void* mu,
+                            const void* rest, const void* A, const void* b, double eps, int not_improved_lim, int max_iter, void* zhat,
                             void* nu, void* lam, void* slack, int32_t* status, int32_t* iters, void* resid,
                             cudaStream_t st) {
   CK(h->d_ph.ensure(sizeof(T) * (size_t)B * (h->n + h->m)));
@@ -681,7 +681,7 @@ static int engine_forward_t(lcpb200_handle_s* h, int B, int nb, int nc, int mode
   c.B = B;
   c.Q = nullptr; c.G = nullptr; c.F = nullptr;
   c.A = (const T*)A; c.b = (const T*)b;
-  fill_soa<T>(c.soa, h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, b1, b2, mu, rest);
+  fill_soa<T>(c.soa, h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, b1, b2, mu, rest, ncs);
   c.p = c.soa.p_s; c.h = c.soa.h_s;
   c.zhat = (T*)zhat; c.nu = (T*)nu; c.lam = (T*)lam; c.slack = (T*)slack; c.resid = (T*)resid;
   c.status = status; c.iters = iters;
@@ -698,8 +698,8 @@ static int engine_forward_t(lcpb200_handle_s* h, int B, int nb, int nc, int mode
 extern "C" int lcpb200_engine_forward(lcpb200_handle_t h, int B, int nb, int nc, int mode, double dt,
                                       const void* mass, const void* inertia, const void* v, const void* fext,
                                       const void* normal, const void* p1, const void* p2, const int32_t* body1,
-                                      const int32_t* body2, const void* mu, const void* restitution, const void* A,
-                                      const void* b, double eps, int not_improved_lim, int max_iter, void* zhat,
+                                      const int32_t* body2, const int32_t* contact_count, const void* mu,
+                                      const void* restitution, const void* A, const void* b, double eps, int not_improved_lim, int max_iter, void* zhat,
                                       void* nu, void* lam, void* slack, int32_t* status, int32_t* iters, void* resid,
                                       void* stream) {
   if (int rc = check_engine(h, B, nb, nc, mode)) return rc;
@@ -712,19 +712,19 @@ extern "C" int lcpb200_engine_forward(lcpb200_handle_t h, int B, int nb, int nc,
   CK(dg_.set(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   return h->dtype == LCPB200_F32
-             ? engine_forward_t<float>(h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, body1, body2, mu,
-                                       restitution, A, b, eps, not_improved_lim, max_iter, zhat, nu, lam, slack, status,
+             ? engine_forward_t<float>(h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, body1, body2,
+                                       contact_count, mu, restitution, A, b, eps, not_improved_lim, max_iter, zhat, nu, lam, slack, status,
                                        iters, resid, st)
-             : engine_forward_t<double>(h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, body1, body2, mu,
-                                        restitution, A, b, eps, not_improved_lim, max_iter, zhat, nu, lam, slack, status,
+             : engine_forward_t<double>(h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, body1, body2,
+                                        contact_count, mu, restitution, A, b, eps, not_improved_lim, max_iter, zhat, nu, lam, slack, status,
                                         iters, resid, st);
 }
 
 template <typename T>
 static int engine_backward_t(lcpb200_handle_s* h, int B, int nb, int nc, int mode, double dt, const void* mass,
                              const void* inertia, const void* v, const void* fext, const void* normal, const void* p1,
-                             const void* p2, const int32_t* b1, const int32_t* b2, const void* mu, const void* rest,
-                             const void* A, const void* zhat, const void* nu, const void* lam, const void* slack,
+                             const void* p2, const int32_t* b1, const int32_t* b2, const int32_t* ncs, const void* mu,
+                             const void* rest, const void* A, const void* zhat, const void* nu, const void* lam, const void* slack,
                              const void* g, void* dmass, void* dinertia, void* dv, void* dfext, void* dnormal,
                              void* dp1, void* dp2, void* dmu, void* drest, void* dA, void* db, unsigned flags,
                              cudaStream_t st) {
@@ -738,7 +738,7 @@ static int engine_backward_t(lcpb200_handle_s* h, int B, int nb, int nc, int mod
   c.dA = (T*)dA; c.db = (T*)db;
   c.done = nullptr; c.only = nullptr; c.flags = flags;
   c.prof = h->cprof;
-  fill_soa<T>(c.soa, h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, b1, b2, mu, rest);
+  fill_soa<T>(c.soa, h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, b1, b2, mu, rest, ncs);
   c.dmass = (T*)dmass; c.dinertia = (T*)dinertia; c.dv = (T*)dv; c.dfext = (T*)dfext; c.dnormal = (T*)dnormal;
   c.dp1 = (T*)dp1; c.dp2 = (T*)dp2; c.dmu = (T*)dmu; c.drest = (T*)drest;
   const int cgrid = std::min(B, h->cond_grid);
@@ -752,8 +752,8 @@ static int engine_backward_t(lcpb200_handle_s* h, int B, int nb, int nc, int mod
 extern "C" int lcpb200_engine_backward(lcpb200_handle_t h, int B, int nb, int nc, int mode, double dt,
                                        const void* mass, const void* inertia, const void* v, const void* fext,
                                        const void* normal, const void* p1, const void* p2, const int32_t* body1,
-                                       const int32_t* body2, const void* mu, const void* restitution, const void* A,
-                                       const void* zhat, const void* nu, const void* lam, const void* slack,
+                                       const int32_t* body2, const int32_t* contact_count, const void* mu,
+                                       const void* restitution, const void* A, const void* zhat, const void* nu, const void* lam, const void* slack,
                                        const void* dl_dzhat, void* dmass, void* dinertia, void* dv, void* dfext,
                                        void* dnormal, void* dp1, void* dp2, void* dmu, void* drestitution, void* dA,
                                        void* db, unsigned flags, void* stream) {
@@ -769,11 +769,11 @@ extern "C" int lcpb200_engine_backward(lcpb200_handle_t h, int B, int nb, int nc
   CK(dg_.set(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   return h->dtype == LCPB200_F32
-             ? engine_backward_t<float>(h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, body1, body2, mu,
-                                        restitution, A, zhat, nu, lam, slack, dl_dzhat, dmass, dinertia, dv, dfext,
+             ? engine_backward_t<float>(h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, body1, body2,
+                                        contact_count, mu, restitution, A, zhat, nu, lam, slack, dl_dzhat, dmass, dinertia, dv, dfext,
                                         dnormal, dp1, dp2, dmu, drestitution, dA, db, flags, st)
-             : engine_backward_t<double>(h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, body1, body2, mu,
-                                         restitution, A, zhat, nu, lam, slack, dl_dzhat, dmass, dinertia, dv, dfext,
+             : engine_backward_t<double>(h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, body1, body2,
+                                         contact_count, mu, restitution, A, zhat, nu, lam, slack, dl_dzhat, dmass, dinertia, dv, dfext,
                                          dnormal, dp1, dp2, dmu, drestitution, dA, db, flags, st);
 }
 

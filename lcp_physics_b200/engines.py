@@ -99,7 +99,8 @@ class _EngineSolveFn(torch.autograd.Function):
     mode 0 = solve_dynamics' LCP (engines.py:50-76), mode 1 = post_stabilization's (engines.py:80-116)."""
 
     @staticmethod
-    def forward(ctx, mass, inertia, v, fext, normal, p1, p2, mu, rest, A, b, body1, body2, dt, mode, max_iter, exact):
+    def forward(ctx, mass, inertia, v, fext, normal, p1, p2, mu, rest, A, b, body1, body2, dt, mode, max_iter, exact,
+                counts=None):
         lib = _lib.load()
         B, nb = mass.shape
         nc = normal.shape[1]
@@ -118,9 +119,9 @@ class _EngineSolveFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.lcpb200_engine_forward(
                 hd.raw, B, nb, nc, int(mode), float(dt), *[_lib.ptr(t) for t in ins], _lib.ptr(body1), _lib.ptr(body2),
-                _lib.ptr(mu_c), _lib.ptr(rest_c), _lib.ptr(A_c), _lib.ptr(b_c), 1e-12, 3, int(max_iter),
+                _lib.ptr(counts), _lib.ptr(mu_c), _lib.ptr(rest_c), _lib.ptr(A_c), _lib.ptr(b_c), 1e-12, 3, int(max_iter),
                 *[_lib.ptr(t) for t in (zhat, nu, lam, slack, status, iters, resid)], _stream_ptr(dev)))
-        ctx.save_for_backward(*ins, mu_c, rest_c, A_c, body1, body2, zhat, nu, lam, slack)
+        ctx.save_for_backward(*ins, mu_c, rest_c, A_c, body1, body2, zhat, nu, lam, slack, counts)
         ctx.meta = (float(dt), int(mode), bool(exact), B, nb, nc, e)
         ctx.mark_non_differentiable(status)
         return zhat, status
@@ -128,7 +129,7 @@ class _EngineSolveFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dzhat, _dstatus):
         lib = _lib.load()
-        (mass, inertia, v, fext, normal, p1, p2, mu, rest, A, body1, body2, zhat, nu, lam, slack) = ctx.saved_tensors
+        (mass, inertia, v, fext, normal, p1, p2, mu, rest, A, body1, body2, zhat, nu, lam, slack, counts) = ctx.saved_tensors
         dt, mode, exact, B, nb, nc, e = ctx.meta
         dev = mass.device
         z = torch.zeros_like
@@ -140,22 +141,23 @@ class _EngineSolveFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.lcpb200_engine_backward(
                 hd.raw, B, nb, nc, mode, dt, *[_lib.ptr(t) for t in (mass, inertia, v, fext, normal, p1, p2)],
-                _lib.ptr(body1), _lib.ptr(body2), _lib.ptr(mu), _lib.ptr(rest), _lib.ptr(A),
+                _lib.ptr(body1), _lib.ptr(body2), _lib.ptr(counts), _lib.ptr(mu), _lib.ptr(rest), _lib.ptr(A),
                 *[_lib.ptr(t) for t in (zhat, nu, lam, slack, dzhat.contiguous())],
                 *[_lib.ptr(t) for t in outs], _lib.ptr(dA), _lib.ptr(db), 1 if exact else 0, _stream_ptr(dev)))
-        return (*outs, dA, db, None, None, None, None, None, None)
+        return (*outs, dA, db, None, None, None, None, None, None, None)
 
 
 def engine_solve(mass, inertia, v, fext, normal, p1, p2, mu, rest, body1, body2, dt, A=None, b=None, mode=0,
-                 max_iter=10, exact_adjoint=False):
+                 max_iter=10, exact_adjoint=False, counts=None):
     """Batched, differentiable LCP of the engine straight from the contact list (CUDA tensors):
     mass/inertia [B,nb], v/fext [B,3nb], normal/p1/p2 [B,nc,2], mu/rest [B,nc], body1/body2 [nc] int32,
     optional equality rows A [B,e,3nb], b [B,e]. Returns (zhat [B,3nb], status [B]); status == -100 marks a
     scene whose topology the fused kernel does not take (use assemble_contacts + LCPFunction for it).
-    solve_dynamics: new_v = -zhat (engines.py:76); post_stabilization: dp = -zhat (engines.py:116)."""
+    solve_dynamics: new_v = -zhat (engines.py:76); post_stabilization: dp = -zhat (engines.py:116).
+    counts [B] int32 (batched worlds): scene s uses its first counts[s] contacts; body1/body2 are then [B,nc]."""
     _lib.require_cuda()
     return _EngineSolveFn.apply(mass, inertia, v, fext, normal, p1, p2, mu, rest, A, b, body1, body2, dt, mode,
-                                max_iter, exact_adjoint)
+                                max_iter, exact_adjoint, counts)
 
 
 class B200PdipmEngine(Engine):

@@ -10,7 +10,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def golden_names():
     return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-                  if not n.startswith("world_") and not n.startswith("seeded_"))
+                  if not n.startswith(("world_", "seeded_", "bworld_")))
 
 
 def seeded_names():
