@@ -157,6 +157,28 @@ def cpu_reference_leg(B_sample, dtype, seed, reps=1, cfg2=False):
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    if args.config == "world":
+        from lcp_physics_b200.scenes import make_ball_drop
+        from oracle.world_oracle import OracleCircleWorld
+        ic = make_ball_drop(1, seed=2000)
+        ow = OracleCircleWorld(ic["pos"][0], ic["rad"][0], ic["vel"][0], ic["mass"][0], ic["rest"][0], ic["fric"][0],
+                               gravity=100.0, static=(0,), dt=1.0 / 30)
+        for _ in range(args.warmup):
+            ow.step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ow.step()
+        dt = time.perf_counter() - t0
+        val = args.steps / dt
+        print(json.dumps({"impl": "reference", "metric": METRIC_WORLD, "value": val, "unit": "world-steps/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": "one world (24 balls + pinned floor ball) stepped on the host"},
+                          "cpu_baseline": {"value": val, "unit": "world-steps/s", "cores": use_all_host_threads(), "kind": "port",
+                                           "sample": "1 world, %d steps (oracle/world_oracle.py)" % args.steps},
+                          "e2e": {"value": val, "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
     cores = use_all_host_threads()
     Bs = args.ref_batch
     cfg2 = args.config == "cfg2"
@@ -224,6 +246,93 @@ def parity_sample(inp_host, g_host, fo_dev, bo_dev, n_sample, dtype, max_iter, w
 
 
 TOL = {torch.float32: 1e-3, torch.float64: 1e-6}
+
+METRIC_WORLD = "sim steps/sec (World.step: 24 balls dropped on a pinned floor ball, 2 fric dirs, fp64; B worlds in lock-step)"
+
+
+def run_world(args, rank, world, local_rank):
+    """--config world: `BatchedWorld.step()` (contact generation + fused engine kernels + dt halving) over B worlds
+    per GPU; value = world-steps per second. CPU baseline: the oracle restatement of the reference's World.step_dt
+    (oracle/world_oracle.py, one world) on the first world of the batch, which also gives the parity figure."""
+    import torch.distributed as dist
+    from lcp_physics_b200 import _lib
+    from lcp_physics_b200.scenes import make_ball_drop
+    from lcp_physics_b200.world import BatchedWorld
+    _lib.require_cuda()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = args.batch or 1024
+    ic = make_ball_drop(B, seed=2000 + rank)
+
+    def mk():
+        return BatchedWorld(ic["pos"], ic["rad"], vel=ic["vel"], mass=ic["mass"], restitution=ic["rest"],
+                            fric_coeff=ic["fric"], gravity=100.0, static=[0], dt=1.0 / 30, device=dev)
+
+    w_ = mk()
+    for _ in range(args.warmup):
+        w_.step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ncs = []
+    for _ in range(args.steps):
+        w_.step()
+        ncs.append(w_.counts.float().mean())
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    # e2e: initial conditions in (pinned) host memory every step-block: upload, K steps, positions back
+    hp = {k: v.pin_memory() for k, v in ic.items()}
+    t0 = time.perf_counter()
+    w2 = BatchedWorld(hp["pos"], hp["rad"], vel=hp["vel"], mass=hp["mass"], restitution=hp["rest"], fric_coeff=hp["fric"],
+                      gravity=100.0, static=[0], dt=1.0 / 30, device=dev)
+    for _ in range(args.steps):
+        w2.step()
+    out_p = w2.p.cpu()
+    e2e_s = time.perf_counter() - t0
+    if rank != 0:
+        return
+    line = {"metric": METRIC_WORLD, "value": world * B * args.steps / (ms * 1e-3), "unit": "world-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BatchedWorld.step(): %d worlds/GPU x (24 balls + pinned floor ball), n=75, <= 75 contacts, "
+                                   "fp64, max_iter=10, per-scene contact sets and dt halving" % B,
+                       "global_batch": world * B, "parallelism": "world-sharded x%d" % world,
+                       "mean_contacts_per_world": float(torch.stack(ncs).mean())},
+            "e2e": {"value": world * B * args.steps / e2e_s, "unit": "world-steps/s",
+                    "h2d_bytes_per_step": sum(v.numel() * 8 for v in ic.values()) // max(1, args.steps),
+                    "d2h_bytes_per_step": out_p.numel() * 8 // max(1, args.steps),
+                    "api": "BatchedWorld(host tensors) -> steps -> positions back to the host"},
+            "gpu_launches": None, "clocks": clocks}
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle.world_oracle import OracleCircleWorld
+        ow = OracleCircleWorld(ic["pos"][0], ic["rad"][0], ic["vel"][0], ic["mass"][0], ic["rest"][0], ic["fric"][0],
+                               gravity=100.0, static=(0,), dt=1.0 / 30)
+        wg = mk()
+        nst = min(args.warmup + args.steps, 40)
+        t0 = time.perf_counter()
+        worst = 0.0
+        for _ in range(nst):
+            ow.step()
+        dt_cpu = time.perf_counter() - t0
+        for _ in range(nst):
+            wg.step()
+        worst = float((wg.p[0].cpu() - ow.p).abs().max())
+        line["parity"] = {"n": 1, "steps": nst, "max_abs_position_error_vs_oracle_world": worst}
+        line["cpu_baseline"] = {"value": nst / dt_cpu, "unit": "world-steps/s", "cores": use_all_host_threads(), "kind": "port",
+                                "sample": "world 0 of the batch, %d steps, %.1f s (oracle/world_oracle.py: restatement of "
+                                          "World.step_dt, LCP by the oracle port)" % (nst, dt_cpu)}
+    print(json.dumps(line), flush=True)
 
 
 def engine_path_leg(B, rank, dev, g, steps, warmup, barrier, world):
@@ -485,7 +594,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="cfg3", choices=["cfg3", "cfg2"],
+    ap.add_argument("--config", default="cfg3", choices=["cfg3", "cfg2", "world"],
                     help="cfg3 (default, BASELINE's headline): fwd+bwd, 4096 x 64 contacts, fp32; "
                          "cfg2: forward only, 1024 x 32 contacts x 3 fric dirs, fp64")
     ap.add_argument("--batch", type=int, default=0, help="scenes per GPU (default: the config's)")
@@ -506,7 +615,10 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     try:
-        run_b200(args, rank, world, local_rank)
+        if args.config == "world":
+            run_world(args, rank, world, local_rank)
+        else:
+            run_b200(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -176,3 +176,30 @@ def make_dense_random(B, n, m, e=0, dtype=torch.float64, seed=0):
         A = torch.tensor([], dtype=f64)
         b = torch.tensor([], dtype=f64)
     return tuple(t.to(dtype).contiguous() for t in (Q, p, G, h, A, b, F))
+
+
+def make_ball_drop(B, nballs=24, cols=6, seed=0, dtype=torch.float64, r_floor=2000.0):
+    """Initial conditions of B `BatchedWorld` scenes: `nballs` balls (radius 20) in a loose cols-wide cluster,
+    dropped onto a huge pinned ball (radius r_floor, body 0) that plays the floor -- the circle-only analogue of
+    the reference's ball-pile demos (demos/demo.py). Returns a dict of [B, ...] tensors for BatchedWorld."""
+    g = torch.Generator().manual_seed(seed)
+    f64 = torch.float64
+    nb = nballs + 1
+    k = torch.arange(nballs)
+    x = 300.0 - 21.0 * (cols - 1) + 42.0 * (k % cols).to(f64)
+    y = 470.0 - 43.0 * (k // cols).to(f64)
+    pos = torch.zeros(B, nb, 2, dtype=f64)
+    pos[:, 0] = torch.tensor([300.0, 500.0 + r_floor], dtype=f64)
+    pos[:, 1:, 0] = x + torch.rand(B, nballs, generator=g, dtype=f64) * 0.8
+    pos[:, 1:, 1] = y - torch.rand(B, nballs, generator=g, dtype=f64) * 3.0
+    vel = torch.zeros(B, nb, 3, dtype=f64)
+    vel[:, 1:] = torch.randn(B, nballs, 3, generator=g, dtype=f64) * torch.tensor([0.2, 5.0, 5.0], dtype=f64)
+    rad = torch.full((B, nb), 20.0, dtype=f64)
+    rad[:, 0] = r_floor
+    mass = torch.ones(B, nb, dtype=f64)
+    mass[:, 1:] = 0.5 + torch.rand(B, nballs, generator=g, dtype=f64)
+    fric = torch.full((B, nb), 0.9, dtype=f64)
+    fric[:, 1:] = 0.2 + 0.7 * torch.rand(B, nballs, generator=g, dtype=f64)
+    rest = torch.full((B, nb), 0.5, dtype=f64)
+    rest[:, 1:] = 0.2 + 0.5 * torch.rand(B, nballs, generator=g, dtype=f64)
+    return {k_: t.to(dtype) for k_, t in dict(pos=pos, vel=vel, rad=rad, mass=mass, fric=fric, rest=rest).items()}

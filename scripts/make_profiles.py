@@ -1,18 +1,25 @@
 """Summarise the ncu captures of one measurement pass into profiles/ (run in the build container).
 
-usage: python scripts/make_profiles.py <tag> <fwd.ncu-rep> <bwd.ncu-rep> <launches.csv> <bench.json>
-The captures come from (on the GPU box, see DESIGN.md section 6):
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline
-  ncu --set full --clock-control none --import-source on -k regex:lcp_forward  -s 1 -c 1 -o fwd python bench.py --steps 1 --warmup 1 --no-cpu-baseline
-  ncu --set full --clock-control none --import-source on -k regex:lcp_backward -s 1 -c 1 -o bwd python bench.py --steps 1 --warmup 1 --no-cpu-baseline
+usage: python scripts/make_profiles.py <tag> <launches.csv> <bench.json> <name>=<rep>:<batch>:<cfg> ...
+e.g.   python scripts/make_profiles.py r02 gpurun_out/r02_launches_raw.csv gpurun_out/bench_r02b.json \
+           fwd=gpurun_out/r02_fwd.ncu-rep:4096:cfg3 bwd=gpurun_out/r02_bwd.ncu-rep:4096:cfg3 \
+           fwd_cfg2=gpurun_out/r02_fwd_cfg2.ncu-rep:1024:cfg2
+The captures come from (on the GPU box):
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline
+  ncu --set full --metrics <local-memory / fp64-pipe counters> --clock-control none --import-source on -k regex:cond_forward -s 1 -c 1 -o fwd python scripts/prof_target.py 4096 cfg3
+  (same with regex:cond_backward ... cfg3 bwd, and regex:cond_forward ... 1024 cfg2)
 """
 import csv, json, shutil, subprocess, sys
 
 KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'launch__grid_size', 'launch__block_size',
-        'launch__registers_per_thread', 'launch__shared_mem_per_block_dynamic', 'sm__cycles_elapsed.max',
+        'launch__registers_per_thread', 'launch__shared_mem_per_block_dynamic', 'launch__occupancy_limit_registers',
+        'launch__occupancy_limit_shared_mem', 'sm__cycles_elapsed.max',
         'smsp__cycles_active.avg', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
-        'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
-        'sm__warps_active.avg.pct_of_peak_sustained_active', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'sm__inst_executed_pipe_fp64.sum', 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
+        'smsp__inst_executed_pipe_fma.sum', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'smsp__inst_executed_op_local_ld.sum', 'smsp__inst_executed_op_local_st.sum',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
         'lts__t_sector_hit_rate.pct', 'dram__throughput.avg.pct_of_peak_sustained_elapsed']
 MULT = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1}
 
@@ -30,32 +37,38 @@ def source_lines(rep):
     hdr = [r for r in rows if r and r[0] == 'Line No'][0]
     idx = {h: i for i, h in enumerate(hdr)}
     st = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
-    cur, agg = None, []
+    cur, agg = None, {}
     for r in rows:
         if not r:
             continue
         if r[0] == 'File Path':
             cur = r[1].split('/')[-1]
-        elif r[0].isdigit():
+        elif r[0].isdigit() and len(r) > 6 and r[2] == '-':
             try:
-                s = int(r[4])
+                s, n = int(r[idx['# Samples']]), int(r[idx['Instructions Executed']])
             except ValueError:
                 continue
-            det = sorted([(int(r[idx[h]]) if r[idx[h]].isdigit() else 0, h.replace('stall_', '')) for h in st], reverse=True)[:3]
-            agg.append((s, cur, int(r[0]), r[1].strip()[:90], det))
+            a = agg.setdefault((cur, int(r[0])), [0, 0, r[1].strip()[:95], {}])
+            a[0] += s; a[1] += n
+            for h in st:
+                v = r[idx[h]]
+                if v.isdigit() and int(v):
+                    a[3][h.replace('stall_', '')] = a[3].get(h.replace('stall_', ''), 0) + int(v)
     return agg
 
 
 def main():
-    tag, fwd, bwd, launches, bench = sys.argv[1:6]
-    for name, rep in (('fwd', fwd), ('bwd', bwd)):
+    tag, launches, bench = sys.argv[1:4]
+    for spec in sys.argv[4:]:
+        name, rest = spec.split('=')
+        rep, batch, cfg = rest.split(':')
         d, u = raw(rep)
         with open('profiles/%s_%s_ncu_summary.txt' % (tag, name), 'w') as f:
-            f.write('# ncu --set full --clock-control none --import-source on -k regex:lcp_%s -s 1 -c 1 python bench.py --steps 1 --warmup 1 --no-cpu-baseline\n' % ('forward' if name == 'fwd' else 'backward'))
-            f.write('# kernel: %s   (B = 4096 scenes, cfg3: n=96 m=256 fp32, one launch)\n' % d.get('Kernel Name'))
+            f.write('# ncu --set full (+ local-memory / fp64-pipe counters) --clock-control none --import-source on, one launch of\n')
+            f.write('# kernel: %s   (B = %s scenes, %s; python scripts/prof_target.py)\n' % (d.get('Kernel Name'), batch, cfg))
             for k in KEYS:
                 if k in d:
-                    f.write('%-70s %s %s\n' % (k, d[k], u.get(k, '')))
+                    f.write('%-72s %s %s\n' % (k, d[k], u.get(k, '')))
             st = {h.replace('smsp__pcsamp_warps_issue_stalled_', ''): int(v) for h, v in d.items()
                   if h.startswith('smsp__pcsamp_warps_issue_stalled_') and 'not_issued' not in h}
             tot = sum(st.values()) or 1
@@ -64,14 +77,18 @@ def main():
                 if v:
                     f.write('%-24s %9d %5.1f%%\n' % (k, v, 100.0 * v / tot))
             agg = source_lines(rep)
-            tot = sum(a[0] for a in agg) or 1
-            f.write('\n# hottest source lines (stall samples, share, top-3 stall reasons)\n')
-            for s, fl, l, sr, det in sorted(agg, reverse=True)[:45]:
-                f.write('%8d %5.1f%% %s:%d  %s | %s\n' % (s, 100.0 * s / tot, fl, l, sr, ' '.join('%s:%d' % (h, v) for v, h in det)))
+            tot = sum(a[0] for a in agg.values()) or 1
+            ti = sum(a[1] for a in agg.values()) or 1
+            f.write('\n# hottest source lines: stall samples, share | warp instructions executed, share | top-3 stall reasons\n')
+            for (fl, l), (s, n, sr, det) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:50]:
+                top = sorted(det.items(), key=lambda x: -x[1])[:3]
+                f.write('%8d %5.1f%% | %10d %5.1f%% | %s:%d  %s | %s\n' % (s, 100.0 * s / tot, n, 100.0 * n / ti, fl, l, sr,
+                                                                          ' '.join('%s:%d' % kv for kv in top)))
         tr = float(d['dram__bytes_read.sum']) * MULT[u['dram__bytes_read.sum']] + float(d['dram__bytes_write.sum']) * MULT[u['dram__bytes_write.sum']]
-        json.dump({'kernel': d.get('Kernel Name'), 'batch': 4096, 'dram_bytes_per_launch': tr,
-                   'duration_ms_under_ncu': float(d['gpu__time_duration.sum'])},
-                  open('profiles/%s_%s_traffic.json' % (tag, name), 'w'))
+        suffix = '' if cfg == 'cfg3' else '_' + cfg
+        json.dump({'kernel': d.get('Kernel Name'), 'batch': int(batch), 'dram_bytes_per_launch': tr,
+                   'duration_ms_under_ncu': float(d['gpu__time_duration.sum']) * {'ms': 1, 'us': 1e-3, 'ns': 1e-6, 's': 1e3}.get(u['gpu__time_duration.sum'], 1)},
+                  open('profiles/%s_%s_traffic%s.json' % (tag, name.replace('_' + cfg, ''), suffix), 'w'))
         print(name, 'dram bytes/launch', tr, 'duration', d['gpu__time_duration.sum'], u['gpu__time_duration.sum'])
     rows = list(csv.reader(open(launches, errors='ignore')))
     hi = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
