@@ -25,7 +25,8 @@ NVCC_FLAGS = [
 
 DUAL_DEPS = ["lcp_kernels.cu", "lcp_launch.h", "lcp_device.cuh", "lcp_lu.cuh", "lcp_solver.cuh"]
 COND_DEPS = ["lcp_cond_kernels.cu", "lcp_cond_launch.h", "lcp_device.cuh", "lcp_condensed.cuh"]
-API_DEPS = ["lcpb200.cu", "lcp_assemble.cuh", "../../include/lcpb200.h"] + DUAL_DEPS[1:] + COND_DEPS[1:]
+BAND_DEPS = ["lcp_band_kernels.cu", "lcp_band_launch.h", "lcp_device.cuh", "lcp_condensed.cuh", "lcp_banded.cuh"]
+API_DEPS = ["lcpb200.cu", "lcp_assemble.cuh", "../../include/lcpb200.h"] + DUAL_DEPS[1:] + COND_DEPS[1:] + BAND_DEPS[1:]
 
 # dual-form kernels: one TU per (dtype, residency mode); condensed kernels: one per (dtype, NS)
 DUAL_VARIANTS = [(t, m) for t in ("float", "double") for m in (0, 1, 2)]
@@ -38,6 +39,7 @@ def _jobs():
         jobs.append(("kernels_%s_m%d.o" % (t, m), "lcp_kernels.cu", ["-DLCP_T=%s" % t, "-DLCP_MODE=%d" % m], DUAL_DEPS))
     for t, ns in COND_VARIANTS:
         jobs.append(("cond_%s_%d.o" % (t, ns), "lcp_cond_kernels.cu", ["-DLCP_T=%s" % t, "-DLCP_NS=%d" % ns], COND_DEPS))
+    jobs.append(("band.o", "lcp_band_kernels.cu", [], BAND_DEPS))
     jobs.append(("api.o", "lcpb200.cu", [], API_DEPS))
     return jobs
 

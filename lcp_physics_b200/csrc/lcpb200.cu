@@ -11,6 +11,7 @@
 #include "lcp_assemble.cuh"
 #include "lcp_launch.h"
 #include "lcp_cond_launch.h"
+#include "lcp_band_launch.h"
 
 using namespace lcpb200;
 using cnd::CPlan;
@@ -65,6 +66,11 @@ struct lcpb200_handle_s {
   int ws_ctas = 0;
   DevBuf d_flag[NSLOT];    // per-scene "gradients already written" flags of the backward pass
   DevBuf d_ph;             // engine path: p and h of every scene ([B,n] + [B,m])
+  bool dual_ok = true;     // false: the dense API is not available for these sizes (engine entry points only)
+  bnd::BPlan bplan;        // banded large-scene kernel (lcp_banded.cuh), planned on the first engine call
+  int bplan_mode = -1;     // mode the plan was made for
+  DevBuf d_bwsd, d_bwsi;   // its per-CTA L2 workspace
+  int bws_ctas = 0;
   // host-buffer pipeline state
   cudaStream_t streams[NSLOT] = {nullptr, nullptr};
   DevBuf d_in[7], d_out[6], d_bwd[16];
@@ -233,9 +239,16 @@ extern "C" int lcpb200_create(int dtype, int n, int m, int e, int device, lcpb20
   }
   int rc = (dtype == LCPB200_F32) ? make_plan<float>(h) : make_plan<double>(h);
   if (!rc) rc = (dtype == LCPB200_F32) ? configure_kernels<float>(h) : configure_kernels<double>(h);
-  if (rc) { delete h; return rc; }
+  if (rc) {
+    // too large for the dense API: the handle still serves the engine entry points (banded kernel, fp64)
+    if (dtype != LCPB200_F64 || n % 3 != 0 || e > bnd::BD) { delete h; return rc; }
+    h->dual_ok = false;
+    h->max_grid = h->num_sms;
+    rc = 0;
+  }
   if (!rc) rc = (dtype == LCPB200_F32) ? make_cplan<float>(h) : make_cplan<double>(h);
   if (rc) { delete h; return rc; }
+  memset(&h->bplan, 0, sizeof(h->bplan));
   *out = h;
   return 0;
 }
@@ -268,6 +281,8 @@ extern "C" int lcpb200_destroy(lcpb200_handle_t h) {
   for (auto& b : h->d_bwd) b.release();
   for (auto& b : h->d_flag) b.release();
   h->d_ph.release();
+  h->d_bwsd.release();
+  h->d_bwsi.release();
   h->d_R.release();
   delete h;
   return 0;
@@ -429,6 +444,7 @@ extern "C" int lcpb200_forward(lcpb200_handle_t h, int B, const void* Q, const v
                                int not_improved_lim, int max_iter, void* zhat, void* nu, void* lam, void* slack,
                                int32_t* status, int32_t* iters, void* resid, void* Rsave, void* stream) {
   if (int rc = check_fwd_args(h, B, Q, p, G, hv, A, b, F, zhat, nu, lam, slack, status, iters, max_iter)) return rc;
+  if (!h->dual_ok) return fail("this handle serves the engine entry points only (problem too large for the dense API)");
   if (B == 0) return 0;
   DeviceGuard dg_;
   CK(dg_.set(h->device));
@@ -445,6 +461,7 @@ extern "C" int lcpb200_backward(lcpb200_handle_t h, int B, const void* Q, const 
                                 const void* slack, const void* g, void* dQ, void* dp, void* dG, void* dh, void* dA,
                                 void* db, void* dF, const void* Rsave, unsigned flags, void* stream) {
   if (!h) return fail("null handle");
+  if (!h->dual_ok) return fail("this handle serves the engine entry points only (problem too large for the dense API)");
   if (B < 0) return fail("B < 0");
   if (!Q || !G || !F || !zhat || !lam || !slack || !g) return fail("Q, G, F, zhat, lam, slack, dl_dzhat must be non-NULL");
   if (h->e > 0 && (!A || !nu)) return fail("A and nu must be non-NULL when e > 0");
@@ -467,7 +484,7 @@ extern "C" int lcpb200_profile(lcpb200_handle_t h, int enable, long long* out) {
   DeviceGuard dg_;
   CK(dg_.set(h->device));
   const size_t cnt = (size_t)lcpb200_handle_s::NSLOT * h->max_grid * PH_COUNT;
-  const size_t ccnt = (size_t)lcpb200_handle_s::NSLOT * std::max(h->cond_grid, 1) * cnd::CPH_COUNT;
+  const size_t ccnt = (size_t)lcpb200_handle_s::NSLOT * std::max(h->cond_grid, h->num_sms) * cnd::CPH_COUNT;
   if (out) {
     for (int i = 0; i < PH_COUNT + cnd::CPH_COUNT; ++i) out[i] = 0;
     if (h->prof) {
@@ -510,6 +527,7 @@ extern "C" int lcpb200_forward_host(lcpb200_handle_t h, int B, const void* Q, co
                                     int not_improved_lim, int max_iter, void* zhat, void* nu, void* lam,
                                     void* slack, int32_t* status, int32_t* iters, void* resid) {
   if (int rc = check_fwd_args(h, B, Q, p, G, hv, A, b, F, zhat, nu, lam, slack, status, iters, max_iter)) return rc;
+  if (!h->dual_ok) return fail("this handle serves the engine entry points only (problem too large for the dense API)");
   if (B == 0) return 0;
   DeviceGuard dg_;
   CK(dg_.set(h->device));
@@ -575,6 +593,7 @@ extern "C" int lcpb200_backward_host(lcpb200_handle_t h, int B, const void* Q, c
                                      const void* slack, const void* g, void* dQ, void* dp, void* dG, void* dh,
                                      void* dA, void* db, void* dF, unsigned flags) {
   if (!h) return fail("null handle");
+  if (!h->dual_ok) return fail("this handle serves the engine entry points only (problem too large for the dense API)");
   if (B < 0) return fail("B < 0");
   // Q == NULL: reuse the device copies (inputs, results and R) that the last forward_host on this
   // handle left behind -- the save_for_backward of lcp.py:34 without a second upload.
@@ -658,11 +677,45 @@ static void fill_soa(cnd::EngineSoA<T>& s, lcpb200_handle_s* h, int B, int nb, i
   s.h_s = s.p_s + (size_t)B * h->n;
 }
 
+// Which kernel family serves the engine entry points of this handle: the condensed-KKT kernels (n + e <= 128,
+// both dtypes) or the banded large-scene kernel (fp64; LCPB200_FORCE_BANDED=1 routes small fp64 scenes there
+// too -- used by the tests to cross-check the two).
+static bool use_banded(const lcpb200_handle_s* h) {
+  if (h->dtype != LCPB200_F64) return false;
+  return !h->cplan.ok || getenv("LCPB200_FORCE_BANDED") != nullptr;
+}
+
+static int ensure_bplan(lcpb200_handle_s* h, int B, int nb, int nc, int mode) {
+  if (h->bplan_mode != mode) {
+    bnd::BPlan& P = h->bplan;
+    memset(&P, 0, sizeof(P));
+    P.nb = nb; P.n = h->n; P.ncap = nc; P.cs = mode == 0 ? 4 : 1; P.m = h->m; P.e = h->e;
+    if (h->e > bnd::BD) return fail("large-scene kernel: more than 16 equality rows");
+    const int dyn_max = h->smem_optin - 1024;
+    if (!bnd::carve_bplan(P, dyn_max)) return fail("large-scene kernel: the scene does not fit (shared memory)");
+    int occ = 0;
+    CK(bnd::configure_band(P.smem_bytes, dyn_max, &occ));
+    if (occ < 1) return fail("large-scene kernel cannot be resident");
+    P.ok = 1;
+    h->bplan_mode = mode;
+    h->bws_ctas = 0;
+  }
+  const int ctas = std::min(B, h->num_sms);
+  if (ctas > h->bws_ctas) {
+    CK(cudaDeviceSynchronize());
+    CK(h->d_bwsd.ensure((size_t)ctas * h->bplan.g_doubles * sizeof(double)));
+    CK(h->d_bwsi.ensure((size_t)ctas * h->bplan.i_ints * sizeof(int)));
+    h->bws_ctas = ctas;
+  }
+  return 0;
+}
+
 static int check_engine(lcpb200_handle_t h, int B, int nb, int nc, int mode) {
   if (!h) return fail("null handle");
   if (B < 0 || nb <= 0 || nc <= 0) return fail("need B >= 0, nb > 0, nc > 0");
   if (mode != 0 && mode != 1) return fail("mode must be 0 (solve_dynamics) or 1 (post_stabilization)");
-  if (!h->cplan.ok) return fail("engine entry points need the condensed-KKT plan (n + e <= 128); use lcpb200_assemble + lcpb200_forward");
+  if (!h->cplan.ok && h->dtype != LCPB200_F64)
+    return fail("engine entry points: n + e > 128 needs the large-scene kernel, which is fp64 only");
   if (h->n != 3 * nb || h->m != (mode == 0 ? 4 : 1) * nc)
     return fail("handle was created for other sizes: need n = 3 nb and m = 4 nc (mode 0) or nc (mode 1)");
   return 0;
@@ -711,6 +764,26 @@ extern "C" int lcpb200_engine_forward(lcpb200_handle_t h, int B, int nb, int nc,
   DeviceGuard dg_;
   CK(dg_.set(h->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_banded(h)) {
+    if (int rc = ensure_bplan(h, B, nb, nc, mode)) return rc;
+    bnd::BArgs a;
+    a.P = h->bplan;
+    a.B = B;
+    memset(&a.soa, 0, sizeof(a.soa));
+    a.soa.mass = (const double*)mass; a.soa.inertia = (const double*)inertia; a.soa.v = (const double*)v;
+    a.soa.fext = (const double*)fext; a.soa.normal = (const double*)normal; a.soa.p1 = (const double*)p1;
+    a.soa.p2 = (const double*)p2; a.soa.mu = (const double*)mu; a.soa.rest = (const double*)restitution;
+    a.soa.b1 = body1; a.soa.b2 = body2; a.soa.nc_s = contact_count; a.soa.nb = nb; a.soa.nc = nc; a.soa.mode = mode;
+    a.soa.dt = dt;
+    a.A = (const double*)A; a.b = (const double*)b;
+    a.zhat = (double*)zhat; a.nu = (double*)nu; a.lam = (double*)lam; a.slack = (double*)slack; a.resid = (double*)resid;
+    a.status = status; a.iters = iters;
+    a.eps = eps; a.not_improved_lim = not_improved_lim; a.max_iter = max_iter;
+    a.wsd = (double*)h->d_bwsd.p; a.wsi = (int*)h->d_bwsi.p;
+    a.prof = h->cprof;
+    CK(bnd::launch_band_forward(a, std::min(B, h->num_sms), st));
+    return 0;
+  }
   return h->dtype == LCPB200_F32
              ? engine_forward_t<float>(h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, body1, body2,
                                        contact_count, mu, restitution, A, b, eps, not_improved_lim, max_iter, zhat, nu, lam, slack, status,
@@ -765,6 +838,7 @@ extern "C" int lcpb200_engine_backward(lcpb200_handle_t h, int B, int nb, int nc
   if (flags != LCPB200_BWD_BUG_COMPATIBLE && flags != LCPB200_BWD_EXACT_ADJOINT)
     return fail("flags must be LCPB200_BWD_BUG_COMPATIBLE or LCPB200_BWD_EXACT_ADJOINT");
   if (B == 0) return 0;
+  if (!h->cplan.ok) return fail("engine_backward: scenes with n + e > 128 (large-scene kernel) have no backward pass yet");
   DeviceGuard dg_;
   CK(dg_.set(h->device));
   cudaStream_t st = (cudaStream_t)stream;

@@ -216,12 +216,16 @@ class B200PdipmEngine(Engine):
 
     def _fused(self, world, dt, fext, Je, ge, dev, mode, max_iter):
         """One lcpb200_engine_forward call for this world (batch of one); None when the fused kernel cannot
-        take it (n + neq > 128, non-diagonal M, vec_len != 3, unsupported topology)."""
+        take it (non-diagonal M, vec_len != 3, unsupported topology, a large scene that is not float64)."""
         M = world.M()
         Md = torch.diagonal(M)
         neq = Je.size(0) if Je.ndimension() > 0 else 0
-        if world.vec_len != 3 or M.size(0) + neq > 128 or len(world.contacts) * 4 > 1024:
+        if world.vec_len != 3:
             return None
+        if M.size(0) + neq > 128 or len(world.contacts) * 4 > 1024:
+            # large scene: banded kernel (fp64, <= 16 border rows); otherwise the dense path
+            if M.dtype != torch.float64 or neq > 16:
+                return None
         if bool((M - torch.diag(Md)).abs().max() != 0):
             return None
         Mb = Md.reshape(-1, 3)

@@ -203,3 +203,29 @@ def make_ball_drop(B, nballs=24, cols=6, seed=0, dtype=torch.float64, r_floor=20
     rest = torch.full((B, nb), 0.5, dtype=f64)
     rest[:, 1:] = 0.2 + 0.5 * torch.rand(B, nballs, generator=g, dtype=f64)
     return {k_: t.to(dtype) for k_, t in dict(pos=pos, vel=vel, rad=rad, mass=mass, fric=fric, rest=rest).items()}
+
+
+def make_ball_pile(B, nballs=512, cols=32, seed=0, dtype=torch.float64, r=10.0, r_floor=1.0e5, gap=0.5):
+    """BASELINE config 4 ("World.step() loop: 512-body ball pile"): `nballs` balls of radius r stacked in a
+    hexagonal grid `cols` wide, `gap` apart, resting just above a huge pinned ball (radius r_floor, body 0)
+    that plays the floor -- the circle-only analogue of the reference's Rect floor (BatchedWorld mirrors
+    circle-circle contacts, contacts.py:68-80). y grows downwards (Gravity is +y, forces.py)."""
+    g = torch.Generator().manual_seed(seed)
+    f64 = torch.float64
+    nb = nballs + 1
+    k = torch.arange(nballs)
+    row, col = k // cols, k % cols
+    pitch = 2 * r + gap
+    x = 500.0 + pitch * (col.to(f64) - (cols - 1) / 2) + (row % 2).to(f64) * (pitch / 2)
+    y = 500.0 - r - gap - row.to(f64) * (pitch * math.sqrt(3) / 2)
+    pos = torch.zeros(B, nb, 2, dtype=f64)
+    pos[:, 0] = torch.tensor([500.0, 500.0 + r_floor], dtype=f64)
+    pos[:, 1:, 0] = x + (torch.rand(B, nballs, generator=g, dtype=f64) - 0.5) * (gap / 4)
+    pos[:, 1:, 1] = y - torch.rand(B, nballs, generator=g, dtype=f64) * (gap / 4)
+    vel = torch.zeros(B, nb, 3, dtype=f64)
+    rad = torch.full((B, nb), r, dtype=f64)
+    rad[:, 0] = r_floor
+    mass = torch.ones(B, nb, dtype=f64)
+    fric = torch.full((B, nb), 0.9, dtype=f64)               # utils.py:22-24 defaults
+    rest = torch.full((B, nb), 0.5, dtype=f64)
+    return {k_: t.to(dtype) for k_, t in dict(pos=pos, vel=vel, rad=rad, mass=mass, fric=fric, rest=rest).items()}
