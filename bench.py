@@ -157,6 +157,26 @@ def cpu_reference_leg(B_sample, dtype, seed, reps=1, cfg2=False):
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    if args.config == "cfg4":
+        ow = cfg4_oracle_world(cfg4_initial(1, 0))
+        for _ in range(min(args.warmup, 1)):                      # ~20 s per step on 8 cores: one warm-up step at most
+            ow.step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ow.step()
+        dt = time.perf_counter() - t0
+        val = args.steps / dt
+        print(json.dumps({"impl": "reference", "metric": METRIC_CFG4, "value": val, "unit": "steps/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": WORKLOAD_CFG4, "worlds": 1, "parallelism": "host CPU, rank 0 only"},
+                          "cpu_baseline": {"value": val, "unit": "steps/s", "cores": use_all_host_threads(), "kind": "port",
+                                           "sample": "%d steps of the 512-ball pile (oracle/world_oracle.py: restatement of "
+                                                     "World.step_dt, LCP by the oracle port, m = 4 x %d contacts)"
+                                                     % (args.steps, len(ow.contacts))},
+                          "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
     if args.config == "world":
         from lcp_physics_b200.scenes import make_ball_drop
         from oracle.world_oracle import OracleCircleWorld
@@ -332,6 +352,142 @@ def run_world(args, rank, world, local_rank):
         line["cpu_baseline"] = {"value": nst / dt_cpu, "unit": "world-steps/s", "cores": use_all_host_threads(), "kind": "port",
                                 "sample": "world 0 of the batch, %d steps, %.1f s (oracle/world_oracle.py: restatement of "
                                           "World.step_dt, LCP by the oracle port)" % (nst, dt_cpu)}
+    print(json.dumps(line), flush=True)
+
+
+# BASELINE.json configs[3] (--config cfg4): "World.step() loop: 512-body ball pile, 2 friction dirs, 1000 steps, 1 GPU"
+CFG4 = dict(nballs=512, cols=32, gap=0.05, gravity=100.0)
+METRIC_CFG4 = "sim steps/sec (World.step() loop, 512-body ball pile, 2 friction dirs, fp64)"
+WORKLOAD_CFG4 = ("BatchedWorld.step() on a pile of 512 balls (radius 10, hexagonal, 32 wide, 0.05 apart: in contact from "
+                 "step 0) resting on a pinned floor ball: n = 1539, ~1450 contacts (m ~ 5800), 2 friction dirs, "
+                 "max_iter = 10, dt = 1/30, fp64; contact generation + LCP + dt halving every step")
+
+
+def cfg4_initial(B, seed):
+    from lcp_physics_b200.scenes import make_ball_pile
+    return make_ball_pile(B, nballs=CFG4["nballs"], cols=CFG4["cols"], seed=3000 + seed, gap=CFG4["gap"])
+
+
+def cfg4_oracle_world(ic, k=0):
+    from oracle.world_oracle import OracleCircleWorld
+    return OracleCircleWorld(ic["pos"][k], ic["rad"][k], ic["vel"][k], ic["mass"][k], ic["rest"][k], ic["fric"][k],
+                             gravity=CFG4["gravity"], static=(0,), dt=1.0 / 30)
+
+
+def run_cfg4(args, rank, world, local_rank):
+    """--config cfg4: the reference's `World.step()` loop on ONE large scene per GPU (`--batch B`: B such worlds per
+    GPU, one CTA each). value = world steps per second (B x steps / time). Every step = batched contact
+    generation (torch ops on the device), one banded-kernel LCP (csrc/lcp_banded.cuh) and the dt-halving loop of
+    world.py:88-107. CPU arm: the oracle restatement of World.step_dt on the same initial condition (one step,
+    ~20 s on 8 cores), which also gives the parity figure."""
+    import torch.distributed as dist
+    from lcp_physics_b200 import _lib
+    from lcp_physics_b200 import engines as _eng
+    from lcp_physics_b200.world import BatchedWorld
+    _lib.require_cuda()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = args.batch or 1
+    ic = cfg4_initial(B, rank)
+
+    def mk(src):
+        return BatchedWorld(src["pos"], src["rad"], vel=src["vel"], mass=src["mass"], restitution=src["rest"],
+                            fric_coeff=src["fric"], gravity=CFG4["gravity"], static=[0], dt=1.0 / 30, device=dev,
+                            contact_capacity=4 * CFG4["nballs"])
+
+    w_ = mk(ic)
+    for _ in range(args.warmup):
+        w_.step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ncs, its = [], []
+    for _ in range(args.steps):
+        w_.step()
+        ncs.append(w_.counts.float().mean())
+        its.append(_eng.last_solve_info()["iters"].float().mean())
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    # the LCP kernel alone (one launch per step): solve_dynamics on the current state, CUDA events
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w_.solve_dynamics(w_.dt)
+    k0.record()
+    for _ in range(5):
+        w_.solve_dynamics(w_.dt)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / 5
+    info = _eng.last_solve_info()
+    iters_k = float(info["iters"].float().mean())
+    hd = _lib.get_handle(torch.float64, w_.n, 4 * w_.cap, w_.ne, dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    hd.profile(True)
+    w_.solve_dynamics(w_.dt)
+    torch.cuda.synchronize()
+    prof = hd.profile(False)
+    bw = prof["c_gradients"] / B                                   # half bandwidth of the ordered condensed matrix (debug counter)
+    # e2e: initial conditions in pinned host memory -> upload, K steps, positions back
+    hp = {k: v.pin_memory() for k, v in ic.items()}
+    t0 = time.perf_counter()
+    w2 = mk(hp)
+    for _ in range(args.steps):
+        w2.step()
+    out_p = w2.p.cpu()
+    e2e_s = time.perf_counter() - t0
+    if rank != 0:
+        return
+    N = w_.n + w_.ne
+    wband = bw + 16                                               # band + border rows each pass touches
+    nfac, nsub = iters_k + 1, 2 * iters_k + 1
+    flops = nfac * 2.0 * N * wband * wband + nsub * 4.0 * N * wband      # banded LU (2 N w^2) + substitutions (4 N w)
+    dense_flops = nfac * (2.0 / 3.0) * (4.0 * float(torch.stack(ncs).mean())) ** 3   # the reference's m x m LU, per solve
+    sms = min(B, torch.cuda.get_device_properties(dev).multi_processor_count)
+    ach = flops * B / (kernel_ms * 1e-3) / 1e12
+    line = {"metric": METRIC_CFG4, "value": world * B * args.steps / (ms * 1e-3), "unit": "steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_CFG4, "worlds_per_gpu": B, "global_worlds": world * B,
+                       "parallelism": "replicas x%d (one scene does not shard)" % world,
+                       "mean_contacts": float(torch.stack(ncs).mean()), "mean_pdipm_iters": float(torch.stack(its).mean()),
+                       "l2": "working set per world (factors + band, ~8 MB) is L2 resident by design; inputs are 60 KB"},
+            "kernel": {"name": "band_forward_kernel", "ms_per_launch": kernel_ms, "launches_per_step": 1,
+                       "share_of_step": kernel_ms / (ms / args.steps), "half_bandwidth": bw, "order": N,
+                       "pdipm_iters": iters_k},
+            "roofline": {"bound": "fma", "achieved": ach, "peak": DFMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / DFMA_PEAK_TFLOPS,
+                         "sms_used": sms, "frac_of_sms_used": ach / (DFMA_PEAK_TFLOPS * sms / 148.0),
+                         "traffic": None,
+                         "note": "achieved = executed banded fp64 flops (2 N w^2 per LU, 4 N w per substitution, w = half "
+                                 "bandwidth + 16 border rows) / kernel time; one CTA per world, so one world uses one SM; "
+                                 "peak = measured DFMA pipe peak of the whole GPU",
+                         "reference_formulation_tflops": dense_flops * B / (kernel_ms * 1e-3) / 1e12},
+            "e2e": {"value": world * B * args.steps / e2e_s, "unit": "steps/s",
+                    "h2d_bytes_per_step": sum(v.numel() * 8 for v in ic.values()) // max(1, args.steps),
+                    "d2h_bytes_per_step": out_p.numel() * 8 // max(1, args.steps),
+                    "api": "BatchedWorld(host tensors) -> steps -> positions back to the host"},
+            "gpu_launches": args.steps, "clocks": clocks}
+    if world == 1 and not args.no_cpu_baseline:
+        ow = cfg4_oracle_world(ic)
+        wg = mk({k: v[:1] for k, v in ic.items()})
+        t0 = time.perf_counter()
+        ow.step()
+        dt_cpu = time.perf_counter() - t0
+        wg.step()
+        line["parity"] = {"n": 1, "steps": 1, "contacts": [int(wg.counts[0]), len(ow.contacts)],
+                          "max_abs_position_error_vs_oracle_world": float((wg.p[0].cpu() - ow.p).abs().max()),
+                          "max_abs_velocity_error_vs_oracle_world": float((wg.v[0].cpu() - ow.v).abs().max())}
+        line["cpu_baseline"] = {"value": 1.0 / dt_cpu, "unit": "steps/s", "cores": use_all_host_threads(), "kind": "port",
+                                "sample": "1 step of world 0 (%d contacts), %.1f s (oracle/world_oracle.py: restatement of "
+                                          "World.step_dt, LCP by the oracle port)" % (len(ow.contacts), dt_cpu)}
     print(json.dumps(line), flush=True)
 
 
@@ -594,9 +750,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="cfg3", choices=["cfg3", "cfg2", "world"],
+    ap.add_argument("--config", default="cfg3", choices=["cfg3", "cfg2", "world", "cfg4"],
                     help="cfg3 (default, BASELINE's headline): fwd+bwd, 4096 x 64 contacts, fp32; "
-                         "cfg2: forward only, 1024 x 32 contacts x 3 fric dirs, fp64")
+                         "cfg2: forward only, 1024 x 32 contacts x 3 fric dirs, fp64; world: BatchedWorld.step() over 1024 "
+                         "small worlds; cfg4: BASELINE configs[3], World.step() loop on one 512-ball pile (fp64, banded kernel)")
     ap.add_argument("--batch", type=int, default=0, help="scenes per GPU (default: the config's)")
     ap.add_argument("--cpu-sample", type=int, default=128)
     ap.add_argument("--ref-batch", type=int, default=256)
@@ -617,6 +774,8 @@ def main():
     try:
         if args.config == "world":
             run_world(args, rank, world, local_rank)
+        elif args.config == "cfg4":
+            run_cfg4(args, rank, world, local_rank)
         else:
             run_b200(args, rank, world, local_rank)
     finally:

@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liblcpb200.so")
+# LCPB200_LIB: load another build of the same library (debug / profiling builds); the default is the in-tree one
+LIB_PATH = os.environ.get("LCPB200_LIB") or os.path.join(_HERE, "csrc", "liblcpb200.so")
 
 F32, F64 = 0, 1
 STATUS_SINGULAR_Q = -1

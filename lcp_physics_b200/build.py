@@ -39,7 +39,8 @@ def _jobs():
         jobs.append(("kernels_%s_m%d.o" % (t, m), "lcp_kernels.cu", ["-DLCP_T=%s" % t, "-DLCP_MODE=%d" % m], DUAL_DEPS))
     for t, ns in COND_VARIANTS:
         jobs.append(("cond_%s_%d.o" % (t, ns), "lcp_cond_kernels.cu", ["-DLCP_T=%s" % t, "-DLCP_NS=%d" % ns], COND_DEPS))
-    jobs.append(("band.o", "lcp_band_kernels.cu", [], BAND_DEPS))
+    # LCPB200_BAND_DEFS: extra -D flags for the banded kernel (debug builds, e.g. -DLCP_BAND_LUPROF)
+    jobs.append(("band.o", "lcp_band_kernels.cu", os.environ.get("LCPB200_BAND_DEFS", "").split(), BAND_DEPS))
     jobs.append(("api.o", "lcpb200.cu", [], API_DEPS))
     return jobs
 

@@ -74,7 +74,7 @@ inline bool carve_bplan(BPlan& P, int smem_limit) {
   take(P.o_up, (size_t)(best + BD) * PV * 8);
   P.o_win = (int)o;
   P.win_bytes = (int)(((long long)smem_limit - (long long)o) & ~15LL);
-  if ((long long)(3 * nb + 1 + 2 * ncap) * 4 > P.win_bytes) return false;
+  if ((long long)(3 * nb + 1 + 2 * ncap) * 4 + 8 + 28LL * nb > P.win_bytes) return false;   // + coordinates / candidate ranks
   P.smem_bytes = (int)o + P.win_bytes;
   long long g = 0;
   auto gt = [&](long long& f, long long cnt) { f = g; g += bal2(cnt); };
@@ -137,7 +137,13 @@ struct Ctx {
   const double* A;
   int nb, n, e, cs, ncap, nc, m;
   int nband, Nb, Nbp, nbb, nbd, bw, bwa, Wc, LDW, LP, fbs, npass, ldk, win_doubles;
+  int o_win, o_sol, o_lp, o_up, o_cf;      // byte offsets of the shared-memory arrays (see smem_d)
 };
+
+// Pointer into the dynamic shared memory, derived from the __shared__ symbol INSIDE the function that uses it: a
+// pointer that travels through Ctx (local memory) is generic, and the hot loops then compile to LD.E / ST.E with
+// every store ordered against the next load (measured: the LU's trailing update ran at 10 DFMA per clock).
+__device__ __forceinline__ double* smem_d(int byte_offset) { return reinterpret_cast<double*>(bnd_smem + byte_offset); }
 
 // position of body `body`'s dof q in `sol` (band part first, then the border)
 __device__ __forceinline__ int sol_index(const Ctx& c, int body, int q) {
@@ -160,6 +166,13 @@ __device__ __noinline__ int build_structure(Ctx& c, const cnd::EngineSoA<double>
   int* queue = mark + nb;
   int* startS = queue + nb;
   int* nbr = startS + nb + 1;
+  // candidate orderings: coordinates of the bodies relative to the root of their component (integrated along the
+  // BFS tree: pos_b2 - pos_b1 = p1 - p2 at a contact), component ids, ranks by x and by y
+  double* px = reinterpret_cast<double*>(mark + ((3 * nb + 1 + 2 * c.ncap + 1) & ~1));
+  double* py = px + nb;
+  int* comp = reinterpret_cast<int*>(py + nb);
+  int* rkx = comp + nb;
+  int* rky = rkx + nb;
   int bad = 0;
   for (int j = tid; j < n; j += NT) {
     const int body = j / 3;
@@ -269,13 +282,13 @@ __device__ __noinline__ int build_structure(Ctx& c, const cnd::EngineSoA<double>
   // ---- breadth-first ordering, level by level (warp 0). Two sweeps per component: the first finds a
   // far (pseudo-peripheral) body, the second, started there, is the ordering.
   if (tid < 32) {
-    int tail = 0;
+    int tail = 0, ncomp = 0;
     for (int root = 0; root < nb; ++root) {
       if (mark[root] != -1) continue;
       int first = root;
       for (int sweep = 0; sweep < 2; ++sweep) {
         const int base = tail;
-        if (lane == 0) { queue[base] = first; mark[first] = base; }
+        if (lane == 0) { queue[base] = first; mark[first] = base; px[first] = 0.0; py[first] = 0.0; comp[first] = ncomp; }
         __syncwarp();
         int hd = base, tl = base + 1, lvl_end = base + 1;
         while (hd < tl) {
@@ -292,7 +305,14 @@ __device__ __noinline__ int build_structure(Ctx& c, const cnd::EngineSoA<double>
             const unsigned same = __match_any_sync(FULL, cand ? w : -1 - lane);
             const bool win = cand && (lane == __ffs(same) - 1);
             const unsigned wb = __ballot_sync(FULL, win);
-            if (win) { const int pos = tl + __popc(wb & ((1u << lane) - 1)); queue[pos] = w; mark[w] = pos; }
+            if (win) {
+              const int pos = tl + __popc(wb & ((1u << lane) - 1));
+              queue[pos] = w; mark[w] = pos; comp[w] = ncomp;
+              const int ad = c.adj[s0 + k], kc = ad >> 1;
+              const double ddx = p1[2 * kc] - p2[2 * kc], ddy = p1[2 * kc + 1] - p2[2 * kc + 1];
+              px[w] = (ad & 1) ? px[u] - ddx : px[u] + ddx;
+              py[w] = (ad & 1) ? py[u] - ddy : py[u] + ddy;
+            }
             tl += __popc(wb);
             __syncwarp();
           }
@@ -308,29 +328,58 @@ __device__ __noinline__ int build_structure(Ctx& c, const cnd::EngineSoA<double>
           tail = tl;
         }
       }
+      ++ncomp;
     }
     if (lane == 0) c.sv[1] = tail;
   }
   __syncthreads();
   const int nband = c.sv[1];
-  int bwb = 0;
-  for (int bq = tid; bq < nb; bq += NT) if (mark[bq] >= 0) c.rank[bq] = mark[bq];
+  // ---- two more candidate orderings: components one after the other, bodies of a component sorted by their x
+  // (resp. y) coordinate (a pile that is long in one direction gets a band as wide as its SHORT side, where the
+  // breadth-first fronts of a hexagonal packing are up to twice as wide). Rank sort, ties by body index.
+  for (int bq = tid; bq < nb; bq += NT) {
+    if (mark[bq] < 0) continue;
+    const int cb = comp[bq];
+    const double xb = px[bq], yb = py[bq];
+    int rx_ = 0, ry_ = 0;
+    for (int o = 0; o < nb; ++o) {
+      if (mark[o] < 0) continue;
+      const int co = comp[o];
+      const double xo = px[o], yo = py[o];
+      const bool cl = co < cb, ce = co == cb;
+      rx_ += (cl || (ce && (xo < xb || (xo == xb && o < bq)))) ? 1 : 0;
+      ry_ += (cl || (ce && (yo < yb || (yo == yb && o < bq)))) ? 1 : 0;
+    }
+    rkx[bq] = rx_; rky[bq] = ry_;
+  }
   __syncthreads();
+  int bw3[3] = {0, 0, 0};
   for (int k = tid; k < nc; k += NT) {
-    const int r1 = c.rank[c.b1[k]], r2 = c.rank[c.b2[k]];
-    if (r1 >= 0 && r2 >= 0) bwb = max(bwb, abs(r1 - r2));
+    const int u1 = c.b1[k], u2 = c.b2[k];
+    if (mark[u1] >= 0 && mark[u2] >= 0) {
+      bw3[0] = max(bw3[0], abs(mark[u1] - mark[u2]));
+      bw3[1] = max(bw3[1], abs(rkx[u1] - rkx[u2]));
+      bw3[2] = max(bw3[2], abs(rky[u1] - rky[u2]));
+    }
   }
   {
-    int vv[1] = {bwb};
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vv[0] = max(vv[0], __shfl_xor_sync(FULL, vv[0], o));
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) bw3[q] = max(bw3[q], __shfl_xor_sync(FULL, bw3[q], o));
     int* ir = reinterpret_cast<int*>(c.red);
-    if (lane == 0) ir[tid >> 5] = vv[0];
+    if (lane == 0) { ir[3 * (tid >> 5)] = bw3[0]; ir[3 * (tid >> 5) + 1] = bw3[1]; ir[3 * (tid >> 5) + 2] = bw3[2]; }
     __syncthreads();
-    bwb = 0;
-    for (int w = 0; w < NT / 32; ++w) bwb = max(bwb, ir[w]);
+    bw3[0] = bw3[1] = bw3[2] = 0;
+    for (int w = 0; w < NT / 32; ++w) { bw3[0] = max(bw3[0], ir[3 * w]); bw3[1] = max(bw3[1], ir[3 * w + 1]); bw3[2] = max(bw3[2], ir[3 * w + 2]); }
     __syncthreads();
   }
+  const int* best = mark;
+  int bwb = bw3[0];
+  if (bw3[1] < bwb) { bwb = bw3[1]; best = rkx; }
+  if (bw3[2] < bwb) { bwb = bw3[2]; best = rky; }
+  for (int bq = tid; bq < nb; bq += NT) if (mark[bq] >= 0) c.rank[bq] = best[bq];
+  __syncthreads();
   c.nband = nband; c.Nb = 3 * nband; c.Nbp = (c.Nb + 7) & ~7;
   c.nbb = nbb; c.nbd = 3 * nbb + e;
   c.bw = 3 * bwb + 2;
@@ -590,13 +639,20 @@ __device__ __forceinline__ void enter_store(const Entering& en, double* win, int
   else win[si * LDW + Wc + lane - BD] = en.br;
 }
 
-__device__ __noinline__ void band_lu(const Ctx& c) {
+// -DLCP_BAND_LUPROF (debug build): split the LU time into diag+D-store / panels / entering loads + update /
+// entering stores, accumulated into the RESID / STEP / POST / RHS counters (subtract their normal values).
+#ifdef LCP_BAND_LUPROF
+#define LUPROF_LAP(ph) pf.lap(ph)
+#else
+#define LUPROF_LAP(ph)
+#endif
+__device__ __noinline__ void band_lu(const Ctx& c, BProf& pf) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Wc = c.Wc, LDW = c.LDW, bwa = c.bwa, Nbp = c.Nbp, LP = c.LP, bw = c.bw, ldk = c.ldk, npass = c.npass;
   const int fbs = c.fbs;
-  double* const win = c.win;
-  double* const lp = c.lp;
-  double* const up = c.up;
+  double* const win = smem_d(c.o_win);
+  double* const lp = smem_d(c.o_lp);
+  double* const up = smem_d(c.o_up);
   double* const FB = c.FB;
   const double* const Kb = c.Kb;
   const double* const KbT = c.KbT;
@@ -649,6 +705,7 @@ __device__ __noinline__ void band_lu(const Ctx& c) {
 #pragma unroll
       for (int p = 0; p < 8; ++p) fb[64 + p] = rd[p];
     }
+    LUPROF_LAP(BPH_RESID);
     // ---- panels: rows of L21 (t < Lr), columns of U12 (Lr <= t < 2 Lr)
     for (int t = tid; t < 2 * Lr; t += NT) {
       const bool isrow = t < Lr;
@@ -680,6 +737,7 @@ __device__ __noinline__ void band_lu(const Ctx& c) {
       }
     }
     __syncthreads();
+    LUPROF_LAP(BPH_STEP);
     // ---- entering row / column of this warp: loads now, stores after the update
     Entering en;
     enter_load(en, Kb, KbT, Brow, Bcol, k0 + Wc + warp, Nbp, ldk, bw, lane);
@@ -700,29 +758,40 @@ __device__ __noinline__ void band_lu(const Ctx& c) {
         for (int p = 0; p < 8; ++p) u8[p][q] = up[p * LP + pr];
       }
       for (int gr = warp; gr < CS; gr += NT / 32) {
+        // 4 x 4 tile: all loads, then 16 independent 8-deep FMA chains, then all stores
+        int roff[4], pr[4];
+        double acc[4][4];
 #pragma unroll
         for (int qr = 0; qr < 4; ++qr) {
           const int rel = gr + qr * CS;
-          int rslot, pr;
-          if (rel < na) { rslot = s0 + PV + rel; if (rslot >= Wc) rslot -= Wc; pr = rel; }
-          else { rslot = Wc + rel - na; pr = bwa + rel - na; }
+          int rslot;
+          if (rel < na) { rslot = s0 + PV + rel; if (rslot >= Wc) rslot -= Wc; pr[qr] = rel; }
+          else { rslot = Wc + rel - na; pr[qr] = bwa + rel - na; }
+          roff[qr] = rslot * LDW;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[qr][q] = win[roff[qr] + cslot[q]];
+        }
+#pragma unroll
+        for (int qr = 0; qr < 4; ++qr) {
           double l8[8];
-          const double2* lsrc = reinterpret_cast<const double2*>(lp + pr * 8);
+          const double2* lsrc = reinterpret_cast<const double2*>(lp + pr[qr] * 8);
 #pragma unroll
           for (int p = 0; p < 4; ++p) { const double2 t2 = lsrc[p]; l8[2 * p] = t2.x; l8[2 * p + 1] = t2.y; }
-          double* wrow = win + rslot * LDW;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            double acc = wrow[cslot[q]];
+          for (int p = 0; p < 8; ++p)
 #pragma unroll
-            for (int p = 0; p < 8; ++p) acc = fma(-l8[p], u8[p][q], acc);
-            wrow[cslot[q]] = acc;
-          }
+            for (int q = 0; q < 4; ++q) acc[qr][q] = fma(-l8[p], u8[p][q], acc[qr][q]);
         }
+#pragma unroll
+        for (int qr = 0; qr < 4; ++qr)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) win[roff[qr] + cslot[q]] = acc[qr][q];
       }
     }
+    LUPROF_LAP(BPH_POST);
     enter_store(en, win, k0 + Wc + warp, s0 + warp, k0 + PV, Nbp, Wc, LDW, bw, lane);
     __syncthreads();
+    LUPROF_LAP(BPH_RHS);
     s0 += PV;
     if (s0 >= Wc) s0 -= Wc;
   }
@@ -736,7 +805,7 @@ __device__ __noinline__ void band_lu(const Ctx& c) {
       if (i > k && j > k) cn[i * LDW + j] = fma(-cn[i * LDW + k], cn[k * LDW + j], cn[i * LDW + j]);
       __syncthreads();
     }
-    c.cf[tid] = cn[i * LDW + j];
+    smem_d(c.o_cf)[tid] = cn[i * LDW + j];
     __syncthreads();
   }
 }
@@ -826,26 +895,27 @@ __device__ __noinline__ void band_solve(const Ctx& c) {
   const int npass = c.npass, fbs = c.fbs;
   const double* const FB = c.FB;
   SolveDims sd;
-  sd.sol = c.sol; sd.bwa = c.bwa; sd.Nbp = c.Nbp; sd.LP = c.LP;
+  sd.sol = smem_d(c.o_sol); sd.bwa = c.bwa; sd.Nbp = c.Nbp; sd.LP = c.LP;
   const int CH = max(1, min(npass, (c.win_doubles / 2) / fbs));             // passes per chunk
   const int nch = (npass + CH - 1) / CH;
-  double* buf[2] = {c.win, c.win + (size_t)CH * fbs};
+  double* const buf0 = smem_d(c.o_win);
+  double* const buf1 = buf0 + (size_t)CH * fbs;
   // ---- forward
-  fetch_chunk(FB, fbs, buf[0], 0, min(CH, npass), tid, NT);
+  fetch_chunk(FB, fbs, buf0, 0, min(CH, npass), tid, NT);
   __syncthreads();
   for (int ch = 0; ch < nch; ++ch) {
     if (warp == 0) {
       const int p_lo = ch * CH, p_hi = min(npass, p_lo + CH);
-      for (int ps = p_lo; ps < p_hi; ++ps) pass_forward(sd, buf[ch & 1] + (size_t)(ps - p_lo) * fbs, ps, lane);
+      for (int ps = p_lo; ps < p_hi; ++ps) pass_forward(sd, ((ch & 1) ? buf1 : buf0) + (size_t)(ps - p_lo) * fbs, ps, lane);
     } else if (ch + 1 < nch) {
-      fetch_chunk(FB, fbs, buf[(ch + 1) & 1], (ch + 1) * CH, min(npass, (ch + 2) * CH), tid - 32, NT - 32);
+      fetch_chunk(FB, fbs, ((ch + 1) & 1) ? buf1 : buf0, (ch + 1) * CH, min(npass, (ch + 2) * CH), tid - 32, NT - 32);
     }
     __syncthreads();
   }
   // ---- corner (16 x 16 dense factors) ; meanwhile the last chunk is already resident for the way back
   if (warp == 0) {
-    const double* const cf = c.cf;
-    double* const solb = c.sol + c.Nbp;
+    const double* const cf = smem_d(c.o_cf);
+    double* const solb = sd.sol + c.Nbp;
     double yi = lane < BD ? solb[lane] : 0.0;
     const int li = lane < BD ? lane : 0;
     for (int k = 0; k < BD; ++k) {
@@ -864,9 +934,9 @@ __device__ __noinline__ void band_solve(const Ctx& c) {
   for (int ch = nch - 1; ch >= 0; --ch) {
     if (warp == 0) {
       const int p_lo = ch * CH, p_hi = min(npass, p_lo + CH);
-      for (int ps = p_hi - 1; ps >= p_lo; --ps) pass_backward(sd, buf[ch & 1] + (size_t)(ps - p_lo) * fbs, ps, lane);
+      for (int ps = p_hi - 1; ps >= p_lo; --ps) pass_backward(sd, ((ch & 1) ? buf1 : buf0) + (size_t)(ps - p_lo) * fbs, ps, lane);
     } else if (ch > 0) {
-      fetch_chunk(FB, fbs, buf[(ch - 1) & 1], (ch - 1) * CH, ch * CH, tid - 32, NT - 32);
+      fetch_chunk(FB, fbs, ((ch - 1) & 1) ? buf1 : buf0, (ch - 1) * CH, ch * CH, tid - 32, NT - 32);
     }
     __syncthreads();
   }
@@ -971,7 +1041,7 @@ __device__ __forceinline__ void factor_kkt(const Ctx& c, BProf& pf, int mode, co
   pf.lap(BPH_WINV);
   assemble_band(c);
   pf.lap(BPH_ASSEMBLE);
-  band_lu(c);
+  band_lu(c, pf);
   pf.lap(BPH_LU);
 }
 
@@ -1165,6 +1235,7 @@ __global__ void __launch_bounds__(NT, 1) band_forward_kernel(const __grid_consta
   c.up = reinterpret_cast<double*>(bnd_smem + P.o_up);
   c.win = reinterpret_cast<double*>(bnd_smem + P.o_win);
   c.win_doubles = P.win_bytes / 8;
+  c.o_win = P.o_win; c.o_sol = P.o_sol; c.o_lp = P.o_lp; c.o_up = P.o_up; c.o_cf = P.o_cf;
   double* g = a.wsd + (size_t)blockIdx.x * P.g_doubles;
   c.qd = g + P.g_qd; c.ps = g + P.g_ps; c.x = g + P.g_x; c.dx = g + P.g_dx; c.rx = g + P.g_rx;
   c.y = g + P.g_y; c.dy = g + P.g_dy; c.ry = g + P.g_ry; c.cg = g + P.g_cg;

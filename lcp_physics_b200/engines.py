@@ -123,6 +123,7 @@ class _EngineSolveFn(torch.autograd.Function):
                 *[_lib.ptr(t) for t in (zhat, nu, lam, slack, status, iters, resid)], _stream_ptr(dev)))
         ctx.save_for_backward(*ins, mu_c, rest_c, A_c, body1, body2, zhat, nu, lam, slack, counts)
         ctx.meta = (float(dt), int(mode), bool(exact), B, nb, nc, e)
+        _last_info.update(iters=iters, resid=resid, status=status, lam=lam, slack=slack)
         ctx.mark_non_differentiable(status)
         return zhat, status
 
@@ -145,6 +146,15 @@ class _EngineSolveFn(torch.autograd.Function):
                 *[_lib.ptr(t) for t in (zhat, nu, lam, slack, dzhat.contiguous())],
                 *[_lib.ptr(t) for t in outs], _lib.ptr(dA), _lib.ptr(db), 1 if exact else 0, _stream_ptr(dev)))
         return (*outs, dA, db, None, None, None, None, None, None, None)
+
+
+_last_info = {}
+
+
+def last_solve_info():
+    """Diagnostics of the most recent engine_solve call (device tensors): PDIPM iteration counts, best residuals,
+    status, multipliers and slacks per scene (the reference prints them with verbose >= 1, pdipm.py:97-105)."""
+    return _last_info
 
 
 def engine_solve(mass, inertia, v, fext, normal, p1, p2, mu, rest, body1, body2, dt, A=None, b=None, mode=0,

@@ -1,5 +1,5 @@
 """GPU: step a ball pile (BASELINE config 4 shape) with BatchedWorld and print the per-phase cycle counters of
-the banded kernel.  usage: band_prof.py nballs cols settle_steps timed_steps [B]"""
+the banded kernel.  usage: band_prof.py nballs cols settle_steps timed_steps [B [gap]]"""
 import os
 import sys
 import time
@@ -13,7 +13,8 @@ from lcp_physics_b200.world import BatchedWorld
 
 nballs, cols, settle, timed = [int(a) for a in sys.argv[1:5]]
 B = int(sys.argv[5]) if len(sys.argv) > 5 else 1
-ic = make_ball_pile(B, nballs=nballs, cols=cols, seed=1)
+gap = float(sys.argv[6]) if len(sys.argv) > 6 else 0.5
+ic = make_ball_pile(B, nballs=nballs, cols=cols, seed=1, gap=gap)
 w = BatchedWorld(ic["pos"].cuda(), ic["rad"].cuda(), vel=ic["vel"].cuda(), mass=ic["mass"].cuda(),
                  restitution=ic["rest"].cuda(), fric_coeff=ic["fric"].cuda(), gravity=100.0, static=(0,),
                  contact_capacity=4 * nballs)
