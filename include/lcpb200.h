@@ -137,6 +137,20 @@ int lcpb200_backward_host(lcpb200_handle_t h, int B,
                           void* dQ, void* dp, void* dG, void* dh, void* dA, void* db, void* dF,
                           unsigned flags);
 
+/* Contact detection for B scenes of nb circles (replaces the pair loop of World.find_contacts,
+ * physics/world.py:139-142, with the circle-circle test of physics/contacts.py:68-80: a pair (i < j) is a
+ * contact iff rad_i + rad_j - |pos_i - pos_j| >= -eps). Device pointers:
+ *   pos[B,nb,2] rad[B,nb]                      body centres and radii (dtype)
+ *   body1[B,cap] body2[B,cap] int32            OUT: the touching pairs of every scene in lexicographic pair
+ *                                              order (the order the reference appends contacts in), padded
+ *                                              with the pair (0, 1)
+ *   counts[B] int32                            OUT: number of touching pairs (may exceed cap: then the lists
+ *                                              hold the first cap pairs and the caller must grow cap)
+ * The contact geometry (normal, p1, p2, penetration) of the selected pairs is the caller's (it is O(cap) and,
+ * in the torch mirror, differentiable). */
+int lcpb200_find_contacts(int dtype, int B, int nb, int cap, double eps, const void* pos, const void* rad,
+                          int32_t* body1, int32_t* body2, int32_t* counts, void* stream);
+
 /* Contact-list -> dense LCP assembly for B scenes of nb bodies (3 dofs each,
  * n = 3 nb), nc contacts, fd = 2 friction directions (world.py:191-192),
  * m = nc (2 + fd). Structure-of-arrays inputs:

@@ -36,6 +36,7 @@ _SIGS = {
                                [ctypes.c_double, ctypes.c_int, ctypes.c_int] + [_vp] * 8),
     "lcpb200_engine_backward": (ctypes.c_int, [_vp] + [ctypes.c_int] * 4 + [ctypes.c_double] + [_vp] * 29 +
                                 [ctypes.c_uint, _vp]),
+    "lcpb200_find_contacts": (ctypes.c_int, [ctypes.c_int] * 4 + [ctypes.c_double] + [_vp] * 6),
     "lcpb200_assemble": (ctypes.c_int, [ctypes.c_int] * 4 + [ctypes.c_double] + [_vp] * 17),
     "lcpb200_assemble_backward": (ctypes.c_int, [ctypes.c_int] * 4 + [ctypes.c_double] + [_vp] * 25),
 }

@@ -639,6 +639,43 @@ __device__ __forceinline__ void enter_store(const Entering& en, double* win, int
   else win[si * LDW + Wc + lane - BD] = en.br;
 }
 
+// 8 x 8 diagonal block at window slots d0 .. d0 + 7: LU without pivoting in registers (every lane of the calling
+// warp redundantly; two pivots per reciprocal pair), published to shared memory for the panel threads:
+// dfac[0..63] = L11 \\ U11 row-major, dfac[64..71] = 1 / diag(U11). (16-byte stores: dfac is 16-byte aligned.)
+__device__ __forceinline__ void factor_diag(const double* win, int LDW, int d0, double* dfac) {
+  double D[8][8], rd[8];
+#pragma unroll
+  for (int p = 0; p < 8; ++p)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) D[p][q] = win[(d0 + p) * LDW + d0 + q];
+#pragma unroll
+  for (int k = 0; k < 8; k += 2) {
+    const double r0 = cnd::rcp64_fast(D[k][k]);
+    const double r1 = D[k][k] * cnd::rcp64_fast(fma(D[k][k], D[k + 1][k + 1], -(D[k + 1][k] * D[k][k + 1])));
+    rd[k] = r0; rd[k + 1] = r1;
+#pragma unroll
+    for (int i = k + 1; i < 8; ++i) {
+      D[i][k] *= r0;
+#pragma unroll
+      for (int j = k + 1; j < 8; ++j) D[i][j] = fma(-D[i][k], D[k][j], D[i][j]);
+    }
+#pragma unroll
+    for (int i = k + 2; i < 8; ++i) {
+      D[i][k + 1] *= r1;
+#pragma unroll
+      for (int j = k + 2; j < 8; ++j) D[i][j] = fma(-D[i][k + 1], D[k + 1][j], D[i][j]);
+    }
+  }
+  // every lane holds the same values and stores them to the same addresses (one wavefront per store)
+  double2* const o = reinterpret_cast<double2*>(dfac);
+#pragma unroll
+  for (int p = 0; p < 8; ++p)
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) o[(p * 8 + q) >> 1] = make_double2(D[p][q], D[p][q + 1]);
+#pragma unroll
+  for (int p = 0; p < 8; p += 2) o[32 + (p >> 1)] = make_double2(rd[p], rd[p + 1]);
+}
+
 // -DLCP_BAND_LUPROF (debug build): split the LU time into diag+D-store / panels / entering loads + update /
 // entering stores, accumulated into the RESID / STEP / POST / RHS counters (subtract their normal values).
 #ifdef LCP_BAND_LUPROF
@@ -667,44 +704,19 @@ __device__ __noinline__ void band_lu(const Ctx& c, BProf& pf) {
     enter_store(en, win, i, i, 0, Nbp, Wc, LDW, bw, lane);
   }
   __syncthreads();
+  if (warp == 0) factor_diag(win, LDW, 0, smem_d(c.o_cf));
+  __syncthreads();
   int s0 = 0;                                                               // slot of pivot k0
   for (int ps = 0; ps < npass; ++ps) {
     const int k0 = PV * ps;
     const int na = min(bwa, Nbp - (k0 + PV));
     const int Lr = na + BD;
     double* const fb = FB + (size_t)ps * fbs;
-    // ---- 8 x 8 diagonal block, factored redundantly by every thread
-    double D[8][8], rd[8];
-#pragma unroll
-    for (int p = 0; p < 8; ++p)
-#pragma unroll
-      for (int q = 0; q < 8; ++q) D[p][q] = win[(s0 + p) * LDW + s0 + q];
-#pragma unroll
-    for (int k = 0; k < 8; k += 2) {
-      const double r0 = cnd::rcp64_fast(D[k][k]);
-      const double r1 = D[k][k] * cnd::rcp64_fast(fma(D[k][k], D[k + 1][k + 1], -(D[k + 1][k] * D[k][k + 1])));
-      rd[k] = r0; rd[k + 1] = r1;
-#pragma unroll
-      for (int i = k + 1; i < 8; ++i) {
-        D[i][k] *= r0;
-#pragma unroll
-        for (int j = k + 1; j < 8; ++j) D[i][j] = fma(-D[i][k], D[k][j], D[i][j]);
-      }
-#pragma unroll
-      for (int i = k + 2; i < 8; ++i) {
-        D[i][k + 1] *= r1;
-#pragma unroll
-        for (int j = k + 2; j < 8; ++j) D[i][j] = fma(-D[i][k + 1], D[k + 1][j], D[i][j]);
-      }
-    }
-    if (tid == NT - 1) {
-#pragma unroll
-      for (int p = 0; p < 8; ++p)
-#pragma unroll
-        for (int q = 0; q < 8; ++q) fb[p * 8 + q] = D[p][q];
-#pragma unroll
-      for (int p = 0; p < 8; ++p) fb[64 + p] = rd[p];
-    }
+    // ---- 8 x 8 diagonal block: dfac[ps & 1] was factored by warp 0 during the previous pass (look-ahead, see the
+    // update phase below); warp 1 copies it to the factor block
+    double* const dfac = smem_d(c.o_cf) + 72 * (ps & 1);                    // (the corner factors land here only after the last pass)
+    if (warp == 1)
+      for (int i = lane; i < 72; i += 32) fb[i] = dfac[i];
     LUPROF_LAP(BPH_RESID);
     // ---- panels: rows of L21 (t < Lr), columns of U12 (Lr <= t < 2 Lr)
     for (int t = tid; t < 2 * Lr; t += NT) {
@@ -720,8 +732,8 @@ __device__ __noinline__ void band_lu(const Ctx& c, BProf& pf) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {                                       // x U11 = a
 #pragma unroll
-          for (int p = 0; p < q; ++p) a[q] = fma(-a[p], D[p][q], a[q]);
-          a[q] *= rd[q];
+          for (int p = 0; p < q; ++p) a[q] = fma(-a[p], dfac[p * 8 + q], a[q]);
+          a[q] *= dfac[64 + q];
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) { lp[pr * 8 + q] = a[q]; fb[72 + q * LP + pr] = a[q]; }
@@ -731,7 +743,7 @@ __device__ __noinline__ void band_lu(const Ctx& c, BProf& pf) {
 #pragma unroll
         for (int p = 1; p < 8; ++p)                                         // L11 y = a
 #pragma unroll
-          for (int q = 0; q < p; ++q) a[p] = fma(-D[p][q], a[q], a[p]);
+          for (int q = 0; q < p; ++q) a[p] = fma(-dfac[p * 8 + q], a[q], a[p]);
 #pragma unroll
         for (int p = 0; p < 8; ++p) { up[p * LP + pr] = a[p]; fb[72 + 8 * LP + p * LP + pr] = a[p]; }
       }
@@ -740,55 +752,86 @@ __device__ __noinline__ void band_lu(const Ctx& c, BProf& pf) {
     LUPROF_LAP(BPH_STEP);
     // ---- entering row / column of this warp: loads now, stores after the update
     Entering en;
+#ifndef LCP_BAND_LATE_ENTER
     enter_load(en, Kb, KbT, Brow, Bcol, k0 + Wc + warp, Nbp, ldk, bw, lane);
-    // ---- trailing update: region index t in [0, Lr) (band rows first, then the border); thread tile = rows
-    // {gr + q CS}, columns {gc + q CS}, q < 4, CS = Lr / 4. A lane keeps its columns' U12 in registers and its
-    // warp walks the row groups.
-    const int CS = Lr >> 2;
-    for (int gc = lane; gc < CS; gc += 32) {
-      int cslot[4];
-      double u8[8][4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int rel = gc + q * CS;
-        int pr;
-        if (rel < na) { cslot[q] = s0 + PV + rel; if (cslot[q] >= Wc) cslot[q] -= Wc; pr = rel; }
-        else { cslot[q] = Wc + rel - na; pr = bwa + rel - na; }
-#pragma unroll
-        for (int p = 0; p < 8; ++p) u8[p][q] = up[p * LP + pr];
-      }
-      for (int gr = warp; gr < CS; gr += NT / 32) {
-        // 4 x 4 tile: all loads, then 16 independent 8-deep FMA chains, then all stores
-        int roff[4], pr[4];
-        double acc[4][4];
-#pragma unroll
-        for (int qr = 0; qr < 4; ++qr) {
-          const int rel = gr + qr * CS;
-          int rslot;
-          if (rel < na) { rslot = s0 + PV + rel; if (rslot >= Wc) rslot -= Wc; pr[qr] = rel; }
-          else { rslot = Wc + rel - na; pr[qr] = bwa + rel - na; }
-          roff[qr] = rslot * LDW;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) acc[qr][q] = win[roff[qr] + cslot[q]];
+#endif
+    LUPROF_LAP(BPH_WINV);
+    // ---- trailing update C -= L21 U12 (rank 8) on the FP64 tensor pipe: the (na + BD)^2 region is cut into
+    // 8 x 8 tiles (a tile's 8 rows / columns are consecutive window slots: s0, Wc and na are multiples of 8, so a
+    // tile never wraps), a warp takes half tile rows and issues two mma.sync.m8n8k4.f64 per tile
+    // (k = pivots 0-3, 4-7) with A = -L21 (lp, [row][8]) and B = U12 (up, [8][LP]). Fragments (PTX ISA, m8n8k4):
+    // A: lane holds (row g, k t), B: (k t, column g), C/D: (row g, columns 2t, 2t + 1), g = lane / 4, t = lane % 4.
+    // One DMMA carries 256 FMAs: 242 instructions per pass instead of 3872 DFMAs, at the same FP64 datapath rate
+    // (measured: 8 warps reach 92 % of the DMMA peak, 54 % of the DFMA peak; profiles/r02_ubench_pipes_latencies.txt).
+    {
+      const int g = lane >> 2, t = lane & 3;
+      const int ntb = na >> 3, ntl = ntb + BD / 8;                          // band tiles, all tiles per dimension
+      const int hc = (ntl + 1) >> 1;
+      // Look-ahead: warp 0 updates tile (0, 0) -- the NEXT diagonal block -- alone, factors it (a serial chain of
+      // ~2000 cycles) and publishes it for the next pass while warps 1..7 do the other tiles.
+      // Work unit of those = half a tile row (2 ntl units); no division, the A fragments stay in registers.
+      if (warp == 0) {
+        if (ps + 1 < npass) {
+          int d0 = s0 + PV; if (d0 >= Wc) d0 -= Wc;
+          const double a0 = -lp[g * 8 + t], a1 = -lp[g * 8 + 4 + t];
+          const double b0 = up[t * LP + g], b1 = up[(4 + t) * LP + g];
+          double* const cptr = win + (d0 + g) * LDW + d0 + 2 * t;
+          double c0 = cptr[0], c1 = cptr[1];
+          asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+              : "+d"(c0), "+d"(c1) : "d"(a0), "d"(b0));
+          asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+              : "+d"(c0), "+d"(c1) : "d"(a1), "d"(b1));
+          cptr[0] = c0; cptr[1] = c1;
+          __syncwarp();
+          factor_diag(win, LDW, d0, smem_d(c.o_cf) + 72 * ((ps + 1) & 1));
         }
+      } else
+      for (int w = warp - 1; w < 2 * ntl; w += NT / 32 - 1) {
+        const int R = w >> 1;
+        const int c_lo = (w & 1) ? hc : ((R == 0 && ps + 1 < npass) ? 1 : 0), c_hi = (w & 1) ? ntl : hc;   // tile (0, 0) is warp 0's
+        int rslot0, rpr0;
+        if (R < ntb) { rslot0 = s0 + PV + 8 * R; if (rslot0 >= Wc) rslot0 -= Wc; rpr0 = 8 * R; }
+        else { rslot0 = Wc + 8 * (R - ntb); rpr0 = bwa + 8 * (R - ntb); }
+        const double a0 = -lp[(rpr0 + g) * 8 + t], a1 = -lp[(rpr0 + g) * 8 + 4 + t];
+        double* const crow = win + (rslot0 + g) * LDW + 2 * t;
+        const double* const ub0 = up + t * LP + g;
+        const double* const ub1 = up + (4 + t) * LP + g;
+        // TB tiles in flight: all operand loads, then the 2 TB DMMAs, then the stores (a tile alone is a serial
+        // chain LDS -> DMMA -> DMMA -> STS of ~200 cycles, and 8 warps do not hide it)
+        constexpr int TB = 3;
+        for (int Cb0 = c_lo; Cb0 < c_hi; Cb0 += TB) {
+          double* cptr[TB];
+          double c0[TB], c1[TB], b0[TB], b1[TB];
+          bool live[TB];
 #pragma unroll
-        for (int qr = 0; qr < 4; ++qr) {
-          double l8[8];
-          const double2* lsrc = reinterpret_cast<const double2*>(lp + pr[qr] * 8);
+          for (int u = 0; u < TB; ++u) {
+            live[u] = Cb0 + u < c_hi;
+            const int Cb = live[u] ? Cb0 + u : Cb0;
+            int cslot0, cpr0;
+            if (Cb < ntb) { cslot0 = s0 + PV + 8 * Cb; if (cslot0 >= Wc) cslot0 -= Wc; cpr0 = 8 * Cb; }
+            else { cslot0 = Wc + 8 * (Cb - ntb); cpr0 = bwa + 8 * (Cb - ntb); }
+            cptr[u] = crow + cslot0;
+            c0[u] = cptr[u][0]; c1[u] = cptr[u][1];
+            b0[u] = ub0[cpr0]; b1[u] = ub1[cpr0];
+          }
 #pragma unroll
-          for (int p = 0; p < 4; ++p) { const double2 t2 = lsrc[p]; l8[2 * p] = t2.x; l8[2 * p + 1] = t2.y; }
+          for (int u = 0; u < TB; ++u)
+            asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                : "+d"(c0[u]), "+d"(c1[u]) : "d"(a0), "d"(b0[u]));
 #pragma unroll
-          for (int p = 0; p < 8; ++p)
+          for (int u = 0; u < TB; ++u)
+            asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                : "+d"(c0[u]), "+d"(c1[u]) : "d"(a1), "d"(b1[u]));
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[qr][q] = fma(-l8[p], u8[p][q], acc[qr][q]);
+          for (int u = 0; u < TB; ++u)
+            if (live[u]) { cptr[u][0] = c0[u]; cptr[u][1] = c1[u]; }
         }
-#pragma unroll
-        for (int qr = 0; qr < 4; ++qr)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) win[roff[qr] + cslot[q]] = acc[qr][q];
       }
     }
     LUPROF_LAP(BPH_POST);
+#ifdef LCP_BAND_LATE_ENTER
+    enter_load(en, Kb, KbT, Brow, Bcol, k0 + Wc + warp, Nbp, ldk, bw, lane);
+#endif
     enter_store(en, win, k0 + Wc + warp, s0 + warp, k0 + PV, Nbp, Wc, LDW, bw, lane);
     __syncthreads();
     LUPROF_LAP(BPH_RHS);

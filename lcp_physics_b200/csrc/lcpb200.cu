@@ -12,6 +12,7 @@
 #include "lcp_launch.h"
 #include "lcp_cond_launch.h"
 #include "lcp_band_launch.h"
+#include "lcp_contacts.cuh"
 
 using namespace lcpb200;
 using cnd::CPlan;
@@ -852,6 +853,24 @@ extern "C" int lcpb200_engine_backward(lcpb200_handle_t h, int B, int nb, int nc
 }
 
 // ------------------------------------------------------------------ assembly
+extern "C" int lcpb200_find_contacts(int dtype, int B, int nb, int cap, double eps, const void* pos, const void* rad,
+                                     int32_t* body1, int32_t* body2, int32_t* counts, void* stream) {
+  if (dtype != LCPB200_F32 && dtype != LCPB200_F64) return fail("bad dtype");
+  if (B < 0 || nb <= 0 || cap <= 0) return fail("find_contacts: need B >= 0, nb > 0, cap > 0");
+  if (!pos || !rad || !body1 || !body2 || !counts) return fail("find_contacts: NULL argument");
+  if (B == 0) return 0;
+  int dev = 0, sms = 0;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LCPB200_F32)
+    cts::launch_find_contacts<float>(B, nb, cap, (float)eps, (const float*)pos, (const float*)rad, body1, body2, counts, sms, st);
+  else
+    cts::launch_find_contacts<double>(B, nb, cap, eps, (const double*)pos, (const double*)rad, body1, body2, counts, sms, st);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int lcpb200_assemble(int dtype, int B, int nb, int nc, double dt, const void* mass, const void* inertia,
                                 const void* v, const void* fext, const void* normal, const void* p1,
                                 const void* p2, const int32_t* body1, const int32_t* body2, const void* mu,

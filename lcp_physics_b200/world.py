@@ -11,9 +11,10 @@ Here the state of B scenes lives in structure-of-arrays tensors on the GPU and o
                                                       world.py:109-120), optional
 
 with contact generation for circle pairs (contacts.py:68-80: normal = (pos1 - pos2)/dist, penetration =
-r1 + r2 - dist, contact when penetration >= -eps, p1 = -n (r1 - pen/2), p2 = n (r2 - pen/2)) as batched
-torch ops on the device, pair order (i < j, lexicographic) as the reference's broadphase callback visits
-them. Every scene keeps its OWN contact count: the fused kernels take a per-scene count, and a scene
+r1 + r2 - dist, contact when penetration >= -eps, p1 = -n (r1 - pen/2), p2 = n (r2 - pen/2)) on the device:
+the pair test and the ordered compaction of all nb (nb - 1) / 2 pairs by lcpb200_find_contacts
+(csrc/lcp_contacts.cuh), pair order (i < j, lexicographic) as the reference's broadphase callback visits
+them, the geometry of the selected pairs by torch ops (differentiable). Every scene keeps its OWN contact count: the fused kernels take a per-scene count, and a scene
 without contacts gets the equality-constrained solve of engines.py:35-49 inside the same kernel.
 
 Scope (what the reference's demos use that this class mirrors): `Circle` bodies (bodies.py:114-140),
@@ -24,6 +25,8 @@ Everything is differentiable through torch autograd (the LCP through lcpb200_eng
 to 42 bodies (3 nb + 3 n_static <= 128); larger scenes (BASELINE config 4: a 512-ball pile) run forward-only
 in float64 through the banded large-scene kernel (csrc/lcp_banded.cuh).
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -87,30 +90,50 @@ class BatchedWorld:
 
     # ------------------------------------------------------------------ contacts.py:68-80, batched
     def find_contacts(self):
+        """Pair test + ordered compaction on the GPU (lcpb200_find_contacts: all nb (nb - 1) / 2 pairs of every
+        scene, lexicographic order = the reference's contact order), then the contact geometry of the selected
+        pairs with torch ops (differentiable w.r.t. the positions)."""
+        lib = _lib.load()
+        B, cap, dev = self.B, self.cap, self.device
         pos = self.p[:, :, 1:]
-        d = pos[:, self.pi] - pos[:, self.pj]                                       # b1.pos - b2.pos
-        dist = d.norm(dim=2)
-        pen = self.rad[:, self.pi] + self.rad[:, self.pj] - dist
-        active = pen >= -self.eps                                                  # `if penetration < -eps: return`
-        counts = active.sum(1)
-        if int(counts.max()) > self.cap:
-            raise RuntimeError("BatchedWorld: a scene has %d contacts, capacity %d" % (int(counts.max()), self.cap))
-        order = torch.sort((~active).to(torch.int8), dim=1, stable=True)[1][:, :self.cap]   # active pairs first, in pair order
-        take = lambda t: torch.gather(t, 1, order)
-        normal = torch.gather(d / dist.unsqueeze(2), 1, order.unsqueeze(2).expand(-1, -1, 2))
-        pen_c = take(pen)
-        b1 = self.pi[order].to(torch.int32)
-        b2 = self.pj[order].to(torch.int32)
-        r1, r2 = take(self.rad[:, self.pi]), take(self.rad[:, self.pj])
-        valid = torch.arange(self.cap, device=self.device).unsqueeze(0) < counts.unsqueeze(1)
+        pos_c = pos.detach().contiguous()
+        b1 = torch.empty(B, cap, dtype=torch.int32, device=dev)
+        b2 = torch.empty(B, cap, dtype=torch.int32, device=dev)
+        counts = torch.empty(B, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.lcpb200_find_contacts(_lib.dtype_code(self.dtype), B, self.nb, cap, self.eps, _lib.ptr(pos_c),
+                                                 _lib.ptr(self.rad), _lib.ptr(b1), _lib.ptr(b2), _lib.ptr(counts),
+                                                 ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        if int(counts.max()) > cap:
+            raise RuntimeError("BatchedWorld: a scene has %d contacts, capacity %d" % (int(counts.max()), cap))
+        i1, i2 = b1.long(), b2.long()
+        take = lambda t, idx: torch.gather(t, 1, idx)
+        d = torch.gather(pos, 1, i1.unsqueeze(2).expand(-1, -1, 2)) - torch.gather(pos, 1, i2.unsqueeze(2).expand(-1, -1, 2))
+        dist = d.norm(dim=2)                                                       # b1.pos - b2.pos   contacts.py:69-71
+        r1, r2 = take(self.rad, i1), take(self.rad, i2)
+        pen_c = r1 + r2 - dist
+        normal = d / dist.unsqueeze(2)
+        valid = torch.arange(cap, device=dev).unsqueeze(0) < counts.unsqueeze(1)
         self.c_normal = normal
-        self.c_p1 = -normal * (r1 - pen_c / 2).unsqueeze(2)
+        self.c_p1 = -normal * (r1 - pen_c / 2).unsqueeze(2)                        # contacts.py:75-77
         self.c_p2 = normal * (r2 - pen_c / 2).unsqueeze(2)
         self.c_pen = torch.where(valid, pen_c, pen_c.new_full((), -1e30))
-        self.c_b1, self.c_b2 = b1.contiguous(), b2.contiguous()
-        self.c_mu = 0.5 * (take(self.fric_coeff[:, self.pi]) + take(self.fric_coeff[:, self.pj]))        # world.py:213-224
-        self.c_rest = 0.5 * (take(self.restitution[:, self.pi]) + take(self.restitution[:, self.pj]))    # world.py:144-151
-        self.counts = counts.to(torch.int32)
+        self.c_b1, self.c_b2 = b1, b2
+        self.c_mu = 0.5 * (take(self.fric_coeff, i1) + take(self.fric_coeff, i2))              # world.py:213-224
+        self.c_rest = 0.5 * (take(self.restitution, i1) + take(self.restitution, i2))          # world.py:144-151
+        self.counts = counts
+
+    def find_contacts_torch(self):
+        """The same contact list with torch ops only (O(nb^2) tensors, a stable sort for the compaction): the
+        independent implementation tests/test_gpu_world.py checks lcpb200_find_contacts against. Returns
+        (counts, b1, b2)."""
+        pos = self.p[:, :, 1:]
+        d = pos[:, self.pi] - pos[:, self.pj]
+        pen = self.rad[:, self.pi] + self.rad[:, self.pj] - d.norm(dim=2)
+        active = pen >= -self.eps                                                  # `if penetration < -eps: return`
+        counts = active.sum(1)
+        order = torch.sort((~active).to(torch.int8), dim=1, stable=True)[1][:, :self.cap]   # active pairs first, in pair order
+        return counts.to(torch.int32), self.pi[order].to(torch.int32), self.pj[order].to(torch.int32)
 
     def max_penetration(self):
         return self.c_pen.max(dim=1)[0]

@@ -43,3 +43,34 @@ def test_batched_world_is_differentiable():
         world.step()
     world.p[:, 1:, 1:].sum().backward()
     assert vel.grad is not None and torch.isfinite(vel.grad).all() and float(vel.grad.abs().max()) > 0
+
+
+@pytest.mark.parametrize("nballs,cols,dtype", [(24, 6, torch.float64), (24, 6, torch.float32), (300, 20, torch.float64)])
+def test_find_contacts_kernel_matches_torch_pair_scan(nballs, cols, dtype):
+    """lcpb200_find_contacts (pair test + ordered compaction, csrc/lcp_contacts.cuh) against the independent torch
+    implementation (all-pairs tensors + stable sort): identical counts and identical ordered pair lists, on
+    loose drops (0..few contacts per scene) and on a dense pile (~850 contacts)."""
+    from lcp_physics_b200.scenes import make_ball_drop, make_ball_pile
+    from lcp_physics_b200.world import BatchedWorld
+    B = 9
+    ic = make_ball_pile(B, nballs=nballs, cols=cols, seed=5, gap=0.05) if nballs > 100 else make_ball_drop(B, nballs=nballs, cols=cols, seed=5)
+    if dtype == torch.float32:
+        ic = {k: v.float() for k, v in ic.items()}
+    w = BatchedWorld(ic["pos"], ic["rad"], vel=ic["vel"], mass=ic["mass"], restitution=ic["rest"], fric_coeff=ic["fric"],
+                     gravity=100.0, static=[0], contact_capacity=4 * nballs)
+    for step in range(6):
+        counts, b1, b2 = w.find_contacts_torch()
+        assert torch.equal(counts, w.counts), (step, counts.tolist(), w.counts.tolist())
+        valid = torch.arange(w.cap, device=w.device).unsqueeze(0) < counts.unsqueeze(1)
+        assert torch.equal(b1[valid], w.c_b1[valid]) and torch.equal(b2[valid], w.c_b2[valid])
+        if nballs > 100:
+            assert int(counts.min()) > 2 * nballs
+        w.step()
+
+
+def test_find_contacts_reports_overflow():
+    from lcp_physics_b200.scenes import make_ball_pile
+    from lcp_physics_b200.world import BatchedWorld
+    ic = make_ball_pile(2, nballs=40, cols=8, seed=1, gap=0.05)
+    with pytest.raises(RuntimeError, match="capacity"):
+        BatchedWorld(ic["pos"], ic["rad"], gravity=100.0, static=[0], contact_capacity=16)
