@@ -62,7 +62,7 @@ inline bool carve_bplan(BPlan& P, int smem_limit) {
   // window (bwa + 8 + BD + 1)^2 doubles + two panels (bwa + BD) x 8; during the structure phase the window
   // region also holds the BFS arrays (3 nb + 1 + 2 ncap ints)
   int best = 0;
-  for (int bwa = 8; bwa <= 1024; bwa += 8) {
+  for (int bwa = 8; bwa <= 128; bwa += 8) {                    // 128 = 32 SUBR rows per substitution round set
     const long long ldw = bwa + PV + BD + 1;
     const long long need = fixed + 2LL * (bwa + BD) * PV * 8 + 32 + ldw * ldw * 8;
     if (need > smem_limit) break;
@@ -492,8 +492,17 @@ __device__ __forceinline__ void k_add(const KStore& c, int ri, int qi, int rj, i
 __device__ __noinline__ void assemble_band(const Ctx& c) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Nbp = c.Nbp, ldk = c.ldk, bw = c.bw;
-  for (size_t t = tid; t < (size_t)Nbp * ldk; t += NT) { c.Kb[t] = 0.0; c.KbT[t] = 0.0; }
-  for (size_t t = tid; t < (size_t)BD * Nbp; t += NT) { c.Brow[t] = 0.0; c.Bcol[t] = 0.0; }
+  {   // zero the arrow storage with 16-byte stores (every array starts 16-byte aligned: bal2 offsets)
+    const double2 z2 = make_double2(0.0, 0.0);
+    const size_t nk = (size_t)Nbp * ldk, nk2 = nk >> 1, nb2 = ((size_t)BD * Nbp) >> 1;      // BD Nbp is even
+    double2* const k2 = reinterpret_cast<double2*>(c.Kb);
+    double2* const kt2 = reinterpret_cast<double2*>(c.KbT);
+    for (size_t t = tid; t < nk2; t += NT) { k2[t] = z2; kt2[t] = z2; }
+    if ((nk & 1) && tid == 0) { c.Kb[nk - 1] = 0.0; c.KbT[nk - 1] = 0.0; }
+    double2* const br2 = reinterpret_cast<double2*>(c.Brow);
+    double2* const bc2 = reinterpret_cast<double2*>(c.Bcol);
+    for (size_t t = tid; t < nb2; t += NT) { br2[t] = z2; bc2[t] = z2; }
+  }
   for (int t = tid; t < BD * BD; t += NT) c.Cn[t] = (t / BD == t % BD && t / BD >= c.nbd) ? 1.0 : 0.0;
   __syncthreads();
   for (int i = c.Nb + tid; i < Nbp; i += NT) c.Kb[(size_t)i * ldk + bw] = 1.0;      // identity padding
@@ -716,7 +725,10 @@ __device__ __noinline__ void band_lu(const Ctx& c, BProf& pf) {
     // update phase below); warp 1 copies it to the factor block
     double* const dfac = smem_d(c.o_cf) + 72 * (ps & 1);                    // (the corner factors land here only after the last pass)
     if (warp == 1)
-      for (int i = lane; i < 72; i += 32) fb[i] = dfac[i];
+      for (int i = lane; i < 72; i += 32) {                                   // the substitutions' copy: U11 rows scaled by 1 / u_pp
+        const int p = i >> 3, q = i & 7;
+        fb[i] = (i < 64 && q > p) ? dfac[i] * dfac[64 + p] : dfac[i];
+      }
     LUPROF_LAP(BPH_RESID);
     // ---- panels: rows of L21 (t < Lr), columns of U12 (Lr <= t < 2 Lr)
     for (int t = tid; t < 2 * Lr; t += NT) {
@@ -868,11 +880,30 @@ __device__ __forceinline__ void fetch_chunk(const double* FB, int fbs, double* d
 
 struct SolveDims { double* sol; int bwa, Nbp, LP; };
 
+// One substitution pass is a latency chain on one warp (8 pivots, then the rows they touch), so the row updates
+// are fully unrolled (SUBR rounds of 32 rows + the border, predicated: all chains in flight together) instead of
+// a loop whose iterations each wait for LDS -> 8 dependent DFMAs -> STS.
+constexpr int SUBR = 4;             // ceil(max bwa / 32); carve_bplan caps bwa at 32 SUBR
+
 __device__ __forceinline__ void pass_forward(const SolveDims c, const double* blk, int ps, int lane) {
   const int k0 = PV * ps, na = min(c.bwa, c.Nbp - (k0 + PV)), LP = c.LP;
   double y[8];
 #pragma unroll
   for (int p = 0; p < 8; ++p) y[p] = c.sol[k0 + p];
+  const double* L = blk + 72;
+  int relc[SUBR];
+  bool ok[SUBR];
+  double acc[SUBR];
+#pragma unroll
+  for (int r = 0; r < SUBR; ++r) {
+    const int rel = lane + 32 * r;
+    ok[r] = rel < na;
+    relc[r] = ok[r] ? rel : 0;
+    acc[r] = c.sol[k0 + PV + relc[r]];
+  }
+  const bool okb = lane < BD;
+  const int lb = c.bwa + (okb ? lane : 0);
+  double accb = c.sol[c.Nbp + (okb ? lane : 0)];
 #pragma unroll
   for (int p = 1; p < 8; ++p)
 #pragma unroll
@@ -881,51 +912,79 @@ __device__ __forceinline__ void pass_forward(const SolveDims c, const double* bl
 #pragma unroll
     for (int p = 0; p < 8; ++p) c.sol[k0 + p] = y[p];
   }
-  const double* L = blk + 72;
-  for (int rel = lane; rel < na; rel += 32) {
-    double acc = c.sol[k0 + PV + rel];
 #pragma unroll
-    for (int p = 0; p < 8; ++p) acc = fma(-L[p * LP + rel], y[p], acc);
-    c.sol[k0 + PV + rel] = acc;
-  }
-  if (lane < BD) {
-    double acc = c.sol[c.Nbp + lane];
+  for (int p = 0; p < 8; ++p) {
 #pragma unroll
-    for (int p = 0; p < 8; ++p) acc = fma(-L[p * LP + c.bwa + lane], y[p], acc);
-    c.sol[c.Nbp + lane] = acc;
+    for (int r = 0; r < SUBR; ++r) acc[r] = fma(-L[p * LP + relc[r]], y[p], acc[r]);
+    accb = fma(-L[p * LP + lb], y[p], accb);
   }
+#pragma unroll
+  for (int r = 0; r < SUBR; ++r)
+    if (ok[r]) c.sol[k0 + PV + relc[r]] = acc[r];
+  if (okb) c.sol[c.Nbp + lane] = accb;
   __syncwarp();
 }
 
+// blk[p * 8 + q], q > p, holds U11[p][q] / U11[p][p] (scaled when the factor block is written), so that the
+// 8-pivot chain is one FMA per step: x_p = (b_p - tail_p) / u_pp - sum_{q > p} (u_pq / u_pp) x_q.
 __device__ __forceinline__ void pass_backward(const SolveDims c, const double* blk, int ps, int lane) {
   const int k0 = PV * ps, na = min(c.bwa, c.Nbp - (k0 + PV)), LP = c.LP;
   const double* U = blk + 72 + 8 * LP;
   double acc[8];
 #pragma unroll
   for (int p = 0; p < 8; ++p) acc[p] = 0.0;
-  for (int rel = lane; rel < na; rel += 32) {
-    const double xv = c.sol[k0 + PV + rel];
 #pragma unroll
-    for (int p = 0; p < 8; ++p) acc[p] = fma(U[p * LP + rel], xv, acc[p]);
+  for (int r = 0; r < SUBR; ++r) {
+    const int rel = lane + 32 * r;
+    const bool ok = rel < na;
+    const int rc = ok ? rel : 0;
+    const double xv = ok ? c.sol[k0 + PV + rc] : 0.0;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) acc[p] = fma(U[p * LP + rc], xv, acc[p]);
   }
-  if (lane < BD) {
-    const double xv = c.sol[c.Nbp + lane];
+  {
+    const bool okb = lane < BD;
+    const int lb = okb ? lane : 0;
+    const double xv = okb ? c.sol[c.Nbp + lb] : 0.0;
 #pragma unroll
-    for (int p = 0; p < 8; ++p) acc[p] = fma(U[p * LP + c.bwa + lane], xv, acc[p]);
+    for (int p = 0; p < 8; ++p) acc[p] = fma(U[p * LP + c.bwa + lb], xv, acc[p]);
   }
+  // 8 sums over 32 lanes: halve the number of values per lane at every butterfly stage (9 exchanges instead of
+  // 40); lane l ends with the total of p = 4 b16 + 2 b8 + b4 (bits of l), then the 8 totals are broadcast
+  double v4[4], v2[2], v1;
+  {
+    const bool hi = lane & 16;
 #pragma unroll
-  for (int p = 0; p < 8; ++p) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[p] += __shfl_xor_sync(FULL, acc[p], o);
+    for (int j = 0; j < 4; ++j) {
+      const double send = hi ? acc[j] : acc[j + 4], keep = hi ? acc[j + 4] : acc[j];
+      v4[j] = keep + __shfl_xor_sync(FULL, send, 16);
+    }
   }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const double send = hi ? v4[j] : v4[j + 2], keep = hi ? v4[j + 2] : v4[j];
+      v2[j] = keep + __shfl_xor_sync(FULL, send, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+    const double send = hi ? v2[0] : v2[1], keep = hi ? v2[1] : v2[0];
+    v1 = keep + __shfl_xor_sync(FULL, send, 4);
+  }
+  v1 += __shfl_xor_sync(FULL, v1, 2);
+  v1 += __shfl_xor_sync(FULL, v1, 1);
   double x[8];
 #pragma unroll
-  for (int p = 7; p >= 0; --p) {
-    double t = c.sol[k0 + p] - acc[p];
-#pragma unroll
-    for (int q = p + 1; q < 8; ++q) t = fma(-blk[p * 8 + q], x[q], t);
-    x[p] = t * blk[64 + p];
+  for (int p = 0; p < 8; ++p) {
+    const double tot = __shfl_sync(FULL, v1, 16 * ((p >> 2) & 1) + 8 * ((p >> 1) & 1) + 4 * (p & 1));
+    x[p] = (c.sol[k0 + p] - tot) * blk[64 + p];
   }
+#pragma unroll
+  for (int p = 6; p >= 0; --p)
+#pragma unroll
+    for (int q = p + 1; q < 8; ++q) x[p] = fma(-blk[p * 8 + q], x[q], x[p]);
   if (lane == 0) {
 #pragma unroll
     for (int p = 0; p < 8; ++p) c.sol[k0 + p] = x[p];
