@@ -7,6 +7,7 @@ namespace lcpb200 {
 namespace bnd {
 
 cudaError_t launch_band_forward(const BArgs& a, int grid, cudaStream_t st);
+cudaError_t launch_band_backward(const BBwdArgs& a, int grid, cudaStream_t st);
 cudaError_t configure_band(int smem_bytes, int dyn_max, int* occ);
 
 }  // namespace bnd

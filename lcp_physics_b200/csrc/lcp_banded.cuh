@@ -87,7 +87,9 @@ inline bool carve_bplan(BPlan& P, int smem_limit) {
   gt(P.g_W, 16LL * ncap); gt(P.g_E, 36LL * ncap);
   const long long ldk = best + 1;
   gt(P.g_Kb, (long long)P.nbp * ldk); gt(P.g_KbT, (long long)P.nbp * ldk);
-  gt(P.g_Brow, (long long)BD * P.nbp); gt(P.g_Bcol, (long long)P.nbp * BD); gt(P.g_Cn, BD * BD);
+  // border rows and columns interleaved: BB[i][0..15] = column i of the border rows, BB[i][16..31] = row i of the
+  // border columns (one 256-byte line per entering index); g_Bcol is kept as the second half's offset
+  gt(P.g_Brow, 2LL * BD * P.nbp); P.g_Bcol = P.g_Brow + (long long)BD * P.nbp; gt(P.g_Cn, BD * BD);
   const long long fbs = 72 + 2LL * PV * (best + BD);
   gt(P.g_FB, (long long)(P.nbp / PV) * fbs + BD * BD);
   P.g_doubles = g;
@@ -112,6 +114,20 @@ struct BArgs {
   double* wsd;                    // [grid][P.g_doubles]
   int* wsi;                       // [grid][P.i_ints]
   long long* prof;                // nullptr or [grid][BPH_COUNT]
+};
+
+// Backward (lcp/lcp.py:37-64) through the engine's assembly for large scenes: saved (zhat, nu, lam, slack) and
+// dl/dzhat in, gradients w.r.t. the contact list out (same outputs as the condensed kernels' engine path).
+struct BBwdArgs {
+  BPlan P;
+  int B;
+  cnd::EngineSoA<double> soa;
+  const double* A;
+  const double *zhat, *nu, *lam, *slack, *g;
+  double *dmass, *dinertia, *dv, *dfext, *dnormal, *dp1, *dp2, *dmu, *drest, *dA, *db;   // any may be nullptr
+  double* wsd;
+  int* wsi;
+  long long* prof;
 };
 
 #ifdef LCP_BAND_DEVICE        // device code: compiled by lcp_band_kernels.cu only
@@ -482,9 +498,9 @@ __device__ __forceinline__ void k_add(const KStore& c, int ri, int qi, int rj, i
     if (j <= i) atomicAdd(&c.Kb[(size_t)i * c.ldk + c.bw - (i - j)], val);
     else atomicAdd(&c.KbT[(size_t)j * c.ldk + c.bw - (j - i)], val);
   } else if (ri >= 0) {
-    atomicAdd(&c.Bcol[(size_t)(3 * ri + qi) * BD + 3 * (-1 - rj) + qj], val);
+    atomicAdd(&c.Brow[(size_t)(3 * ri + qi) * (2 * BD) + BD + 3 * (-1 - rj) + qj], val);
   } else if (rj >= 0) {
-    atomicAdd(&c.Brow[(size_t)(3 * (-1 - ri) + qi) * c.Nbp + 3 * rj + qj], val);
+    atomicAdd(&c.Brow[(size_t)(3 * rj + qj) * (2 * BD) + 3 * (-1 - ri) + qi], val);
   }
 }
 
@@ -494,14 +510,13 @@ __device__ __noinline__ void assemble_band(const Ctx& c) {
   const int Nbp = c.Nbp, ldk = c.ldk, bw = c.bw;
   {   // zero the arrow storage with 16-byte stores (every array starts 16-byte aligned: bal2 offsets)
     const double2 z2 = make_double2(0.0, 0.0);
-    const size_t nk = (size_t)Nbp * ldk, nk2 = nk >> 1, nb2 = ((size_t)BD * Nbp) >> 1;      // BD Nbp is even
+    const size_t nk = (size_t)Nbp * ldk, nk2 = nk >> 1, nb2 = (size_t)BD * Nbp;             // interleaved border: 2 BD Nbp doubles
     double2* const k2 = reinterpret_cast<double2*>(c.Kb);
     double2* const kt2 = reinterpret_cast<double2*>(c.KbT);
     for (size_t t = tid; t < nk2; t += NT) { k2[t] = z2; kt2[t] = z2; }
     if ((nk & 1) && tid == 0) { c.Kb[nk - 1] = 0.0; c.KbT[nk - 1] = 0.0; }
     double2* const br2 = reinterpret_cast<double2*>(c.Brow);
-    double2* const bc2 = reinterpret_cast<double2*>(c.Bcol);
-    for (size_t t = tid; t < nb2; t += NT) { br2[t] = z2; bc2[t] = z2; }
+    for (size_t t = tid; t < nb2; t += NT) br2[t] = z2;
   }
   for (int t = tid; t < BD * BD; t += NT) c.Cn[t] = (t / BD == t % BD && t / BD >= c.nbd) ? 1.0 : 0.0;
   __syncthreads();
@@ -616,7 +631,7 @@ __device__ __forceinline__ void enter_load(Entering& en, const double* __restric
     en.row[q] = (ent && u <= bw) ? Kb[(size_t)i * ldk + u] : 0.0;
     en.col[q] = (ent && u < bw) ? KbT[(size_t)i * ldk + u] : 0.0;
   }
-  en.br = ent ? (lane < BD ? Brow[(size_t)lane * Nbp + i] : Bcol[(size_t)i * BD + lane - BD]) : 0.0;
+  en.br = ent ? Brow[(size_t)i * (2 * BD) + lane] : 0.0;                    // interleaved border storage: one line
 }
 
 // si: slot of i. Entries with a negative partner index (initial fill) are skipped.
@@ -1325,9 +1340,7 @@ __device__ __forceinline__ void forward_scene(const BArgs& a, Ctx& c, BProf& pf,
   if (tid == 0) { a.status[sc] = status; a.iters[sc] = it; if (a.resid) a.resid[sc] = best; }
 }
 
-__global__ void __launch_bounds__(NT, 1) band_forward_kernel(const __grid_constant__ BArgs a) {
-  const BPlan& P = a.P;
-  Ctx c;
+__device__ __forceinline__ void init_ctx(Ctx& c, const BPlan& P, double* wsd, int* wsi) {
   c.red = reinterpret_cast<double*>(bnd_smem + P.o_red);
   c.sv = reinterpret_cast<int*>(bnd_smem + P.o_sv);
   c.rank = reinterpret_cast<int*>(bnd_smem + P.o_rank);
@@ -1338,15 +1351,21 @@ __global__ void __launch_bounds__(NT, 1) band_forward_kernel(const __grid_consta
   c.win = reinterpret_cast<double*>(bnd_smem + P.o_win);
   c.win_doubles = P.win_bytes / 8;
   c.o_win = P.o_win; c.o_sol = P.o_sol; c.o_lp = P.o_lp; c.o_up = P.o_up; c.o_cf = P.o_cf;
-  double* g = a.wsd + (size_t)blockIdx.x * P.g_doubles;
+  double* g = wsd + (size_t)blockIdx.x * P.g_doubles;
   c.qd = g + P.g_qd; c.ps = g + P.g_ps; c.x = g + P.g_x; c.dx = g + P.g_dx; c.rx = g + P.g_rx;
   c.y = g + P.g_y; c.dy = g + P.g_dy; c.ry = g + P.g_ry; c.cg = g + P.g_cg;
   c.z = g + P.g_z; c.s = g + P.g_s; c.d = g + P.g_d; c.rz = g + P.g_rz; c.rs = g + P.g_rs; c.dz = g + P.g_dz;
   c.ds = g + P.g_ds; c.t = g + P.g_t; c.h = g + P.g_h; c.W = g + P.g_W; c.E = g + P.g_E;
   c.Kb = g + P.g_Kb; c.KbT = g + P.g_KbT; c.Brow = g + P.g_Brow; c.Bcol = g + P.g_Bcol; c.Cn = g + P.g_Cn; c.FB = g + P.g_FB;
-  int* gi = a.wsi + (size_t)blockIdx.x * P.i_ints;
+  int* gi = wsi + (size_t)blockIdx.x * P.i_ints;
   c.deg = gi + P.i_deg; c.start = gi + P.i_start; c.adj = gi + P.i_adj;
   c.nb = P.nb; c.n = P.n; c.e = P.e; c.cs = P.cs; c.ncap = P.ncap;
+}
+
+__global__ void __launch_bounds__(NT, 1) band_forward_kernel(const __grid_constant__ BArgs a) {
+  const BPlan& P = a.P;
+  Ctx c;
+  init_ctx(c, P, a.wsd, a.wsi);
   BProf pf;
   pf.start(a.prof ? a.prof + (size_t)blockIdx.x * BPH_COUNT : nullptr);
   for (int sc = blockIdx.x; sc < a.B; sc += gridDim.x) {
@@ -1363,6 +1382,153 @@ __global__ void __launch_bounds__(NT, 1) band_forward_kernel(const __grid_consta
       if (threadIdx.x == 0) { a.status[sc] = rc == 2 ? -1 : STATUS_UNSUPPORTED; a.iters[sc] = 0; if (a.resid) a.resid[sc] = nan(""); }
     } else {
       forward_scene(a, c, pf, sc);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ backward (lcp.py:37-64), one scene
+// One factorisation at d = lam / slack (clamped to [1e-10, 1e10] like the condensed fp64 backward, DESIGN.md
+// section 3.1), one solve with the right-hand side (dl/dzhat, 0, 0, 0), then the chain rule through the assembly
+// (world.py:144-234, engines.py:50-116) applied to the factored gradients of lcp.py:52-63 -- evaluated only at
+// the entries the assembly writes (same formulas as lcp_condensed.cuh's engine path; bug-compatible adjoint).
+__device__ __forceinline__ void backward_scene(const BBwdArgs& a, Ctx& c, BProf& pf, int sc) {
+  const int tid = threadIdx.x, n = c.n, e = c.e, nc = c.nc, cs = c.cs, ncap = c.ncap, nb = c.nb;
+  const cnd::EngineSoA<double>& E = a.soa;
+  const int ncs = E.nc, mode = E.mode;
+  const double* mu = E.mu ? E.mu + (size_t)sc * ncs : nullptr;
+  const double* zh = a.zhat + (size_t)sc * n;
+  const double* lamv = a.lam + (size_t)sc * a.P.m;
+  const double* slk = a.slack + (size_t)sc * a.P.m;
+  for (int i = tid; i < n; i += NT) { c.x[i] = zh[i]; c.rx[i] = a.g[(size_t)sc * n + i]; }
+  for (int r = 0; r < cs; ++r)
+    for (int k = tid; k < nc; k += NT) {
+      const int i = r * ncap + k, o = out_row(r, k, nc);
+      double d = lamv[o] / slk[o];                                          // :44
+      d = d > 1e10 ? 1e10 : (d < 1e-10 ? 1e-10 : d);
+      c.z[i] = lamv[o]; c.s[i] = slk[o]; c.d[i] = d; c.rs[i] = 0.0;
+    }
+  for (int i = tid; i < e; i += NT) c.y[i] = a.nu[(size_t)sc * e + i];
+  __syncthreads();
+  factor_kkt(c, pf, mode, mu);                                              // :46
+  solve_kkt(c, pf, c.rx, c.rs, nullptr, nullptr, c.dx, c.ds, c.dz, c.dy);   // :47-50
+  const double* dx = c.dx;
+  const double* dlam = c.dz;
+  const double* lm = c.z;
+  const double* v = E.v + (size_t)sc * n;
+  for (int k = tid; k < ncs; k += NT) {
+    const size_t ic = (size_t)sc * ncs + k;
+    if (k >= nc) {                                                          // unused slots of a scene with fewer contacts
+      if (a.dnormal) { a.dnormal[ic * 2] = 0; a.dnormal[ic * 2 + 1] = 0; }
+      if (a.dp1) { a.dp1[ic * 2] = 0; a.dp1[ic * 2 + 1] = 0; }
+      if (a.dp2) { a.dp2[ic * 2] = 0; a.dp2[ic * 2 + 1] = 0; }
+      if (a.drest) a.drest[ic] = 0;
+      if (a.dmu) a.dmu[ic] = 0;
+      continue;
+    }
+    const double nx = E.normal[ic * 2], ny = E.normal[ic * 2 + 1];
+    const double p1x = E.p1[ic * 2], p1y = E.p1[ic * 2 + 1], p2x = E.p2[ic * 2], p2y = E.p2[ic * 2 + 1];
+    const int j1 = 3 * c.b1[k], j2 = 3 * c.b2[k];
+    const double rc = E.rest[ic];
+    const double dhc = -dlam[k];                                            // dh = -dlam  (:55)
+    double gnx = 0, gny = 0, g1x = 0, g1y = 0, g2x = 0, g2y = 0, jcv = 0;
+    const int nrows = mode == 0 ? 3 : 1;
+    for (int q = 0; q < nrows; ++q) {
+      const double ddx_ = q == 0 ? nx : (q == 1 ? ny : -ny), ddy_ = q == 0 ? ny : (q == 1 ? -nx : nx);
+      const double dl = dlam[q * ncap + k], lq = lm[q * ncap + k];
+      double g[6];
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        g[t] = dl * zh[j1 + t] + lq * dx[j1 + t];                           // dG[i][j1 + t]  (:53)
+        g[3 + t] = dl * zh[j2 + t] + lq * dx[j2 + t];
+      }
+      if (q == 0) {
+        const double row[6] = {p1x * ddy_ - p1y * ddx_, ddx_, ddy_, -(p2x * ddy_ - p2y * ddx_), -ddx_, -ddy_};
+#pragma unroll
+        for (int t = 0; t < 3; ++t) jcv += row[t] * v[j1 + t] + row[3 + t] * v[j2 + t];
+        const double hs_ = mode == 0 ? rc : (1.0 - rc);                     // h_c = (Jc v) rest  |  (Jc v)(1 - rest)
+#pragma unroll
+        for (int t = 0; t < 3; ++t) { g[t] += dhc * hs_ * v[j1 + t]; g[3 + t] += dhc * hs_ * v[j2 + t]; }
+      }
+      const double gdx = -p1y * g[0] + g[1] + p2y * g[3] - g[4];
+      const double gdy = p1x * g[0] + g[2] - p2x * g[3] - g[5];
+      g1x += ddy_ * g[0]; g1y += -ddx_ * g[0];
+      g2x += -ddy_ * g[3]; g2y += ddx_ * g[3];
+      if (q == 0) { gnx += gdx; gny += gdy; }
+      else if (q == 1) { gny += gdx; gnx += -gdy; }                         // dir1 = (ny, -nx)
+      else { gny += -gdx; gnx += gdy; }                                     // dir2 = (-ny, nx)
+    }
+    if (a.dnormal) { a.dnormal[ic * 2] = gnx; a.dnormal[ic * 2 + 1] = gny; }
+    if (a.dp1) { a.dp1[ic * 2] = g1x; a.dp1[ic * 2 + 1] = g1y; }
+    if (a.dp2) { a.dp2[ic * 2] = g2x; a.dp2[ic * 2 + 1] = g2y; }
+    if (a.drest) a.drest[ic] = mode == 0 ? dhc * jcv : -dhc * jcv;
+    if (a.dmu) a.dmu[ic] = mode == 0 ? -(dlam[3 * ncap + k] * lm[k]) : 0.0;   // dF[gamma_c][c]  (:54)
+  }
+  for (int body = tid; body < nb; body += NT) {
+    double dm = 0.0;
+    const int s0 = c.start[body], s1 = c.start[body + 1];
+#pragma unroll
+    for (int comp = 0; comp < 3; ++comp) {
+      const int j = 3 * body + comp;
+      const double md = comp == 0 ? E.inertia[(size_t)sc * nb + body] : E.mass[(size_t)sc * nb + body];
+      const double dpj = mode == 0 ? dx[j] : 0.0;                           // dp = dx (:52); post-stabilisation has p = 0
+      if (a.dfext) a.dfext[(size_t)sc * n + j] = E.dt * dpj;
+      if (a.dv) {
+        double acc = md * dpj;
+        for (int it = s0; it < s1; ++it) {                                  // the contacts that touch this body
+          const int ad = c.adj[it], k = ad >> 1, side = ad & 1;
+          const double hs_ = mode == 0 ? E.rest[(size_t)sc * ncs + k] : (1.0 - E.rest[(size_t)sc * ncs + k]);
+          acc += -dlam[k] * hs_ * c.cg[12 * (size_t)k + 3 * side + comp];  // dh_c d(h_c)/dv_j
+        }
+        a.dv[(size_t)sc * n + j] = acc;
+      }
+      const double dq = dx[j] * zh[j] + dpj * v[j];                         // dQ_jj = 1/2 (dx_j z_j + z_j dx_j)  (:61), dp_j d(p_j)/dM_jj
+      if (comp == 0) { if (a.dinertia) a.dinertia[(size_t)sc * nb + body] = dq; }
+      else dm += dq;
+    }
+    if (a.dmass) a.dmass[(size_t)sc * nb + body] = dm;
+  }
+  if (a.db && e > 0) for (int i = tid; i < e; i += NT) a.db[(size_t)sc * e + i] = -c.dy[i];
+  if (a.dA && e > 0) {
+    double* o = a.dA + (size_t)sc * e * n;
+    for (int i = 0; i < e; ++i)
+      for (int j = tid; j < n; j += NT) o[(size_t)i * n + j] = c.dy[i] * zh[j] + c.y[i] * dx[j];
+  }
+  __syncthreads();
+  pf.lap(BPH_GRADS);
+}
+
+__global__ void __launch_bounds__(NT, 1) band_backward_kernel(const __grid_constant__ BBwdArgs a) {
+  const BPlan& P = a.P;
+  Ctx c;
+  init_ctx(c, P, a.wsd, a.wsi);
+  BProf pf;
+  pf.start(a.prof ? a.prof + (size_t)blockIdx.x * BPH_COUNT : nullptr);
+  for (int sc = blockIdx.x; sc < a.B; sc += gridDim.x) {
+    const int ncs = a.soa.nc, n = P.n, nb = P.nb, e = P.e;
+    c.nc = a.soa.nc_s ? a.soa.nc_s[sc] : ncs;
+    c.b1 = a.soa.b1 + (a.soa.nc_s ? (size_t)sc * ncs : 0);
+    c.b2 = a.soa.b2 + (a.soa.nc_s ? (size_t)sc * ncs : 0);
+    c.A = e > 0 ? a.A + (size_t)sc * e * n : nullptr;
+    int rc = (c.nc < 0 || c.nc > P.ncap) ? 1 : 0;
+    if (rc == 0) { c.m = c.cs * c.nc; rc = build_structure(c, a.soa, sc); }
+    pf.lap(BPH_STRUCT);
+    if (rc != 0) {                                                          // the forward reported it: zero gradients
+      const int tid = threadIdx.x;
+      for (int i = tid; i < n; i += NT) { if (a.dv) a.dv[(size_t)sc * n + i] = 0; if (a.dfext) a.dfext[(size_t)sc * n + i] = 0; }
+      for (int i = tid; i < nb; i += NT) { if (a.dmass) a.dmass[(size_t)sc * nb + i] = 0; if (a.dinertia) a.dinertia[(size_t)sc * nb + i] = 0; }
+      for (int i = tid; i < ncs; i += NT) {
+        const size_t ic = (size_t)sc * ncs + i;
+        if (a.dnormal) { a.dnormal[ic * 2] = 0; a.dnormal[ic * 2 + 1] = 0; }
+        if (a.dp1) { a.dp1[ic * 2] = 0; a.dp1[ic * 2 + 1] = 0; }
+        if (a.dp2) { a.dp2[ic * 2] = 0; a.dp2[ic * 2 + 1] = 0; }
+        if (a.drest) a.drest[ic] = 0;
+        if (a.dmu) a.dmu[ic] = 0;
+      }
+      for (int i = tid; i < e; i += NT) if (a.db) a.db[(size_t)sc * e + i] = 0;
+      if (a.dA) for (int i = tid; i < e * n; i += NT) a.dA[(size_t)sc * e * n + i] = 0;
+    } else {
+      backward_scene(a, c, pf, sc);
     }
     __syncthreads();
   }

@@ -839,10 +839,32 @@ extern "C" int lcpb200_engine_backward(lcpb200_handle_t h, int B, int nb, int nc
   if (flags != LCPB200_BWD_BUG_COMPATIBLE && flags != LCPB200_BWD_EXACT_ADJOINT)
     return fail("flags must be LCPB200_BWD_BUG_COMPATIBLE or LCPB200_BWD_EXACT_ADJOINT");
   if (B == 0) return 0;
-  if (!h->cplan.ok) return fail("engine_backward: scenes with n + e > 128 (large-scene kernel) have no backward pass yet");
   DeviceGuard dg_;
   CK(dg_.set(h->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_banded(h)) {
+    if (flags != LCPB200_BWD_BUG_COMPATIBLE) return fail("engine_backward: the large-scene kernel implements the bug-compatible adjoint only");
+    if (int rc = ensure_bplan(h, B, nb, nc, mode)) return rc;
+    bnd::BBwdArgs a;
+    a.P = h->bplan;
+    a.B = B;
+    memset(&a.soa, 0, sizeof(a.soa));
+    a.soa.mass = (const double*)mass; a.soa.inertia = (const double*)inertia; a.soa.v = (const double*)v;
+    a.soa.fext = (const double*)fext; a.soa.normal = (const double*)normal; a.soa.p1 = (const double*)p1;
+    a.soa.p2 = (const double*)p2; a.soa.mu = (const double*)mu; a.soa.rest = (const double*)restitution;
+    a.soa.b1 = body1; a.soa.b2 = body2; a.soa.nc_s = contact_count; a.soa.nb = nb; a.soa.nc = nc; a.soa.mode = mode;
+    a.soa.dt = dt;
+    a.A = (const double*)A;
+    a.zhat = (const double*)zhat; a.nu = (const double*)nu; a.lam = (const double*)lam; a.slack = (const double*)slack;
+    a.g = (const double*)dl_dzhat;
+    a.dmass = (double*)dmass; a.dinertia = (double*)dinertia; a.dv = (double*)dv; a.dfext = (double*)dfext;
+    a.dnormal = (double*)dnormal; a.dp1 = (double*)dp1; a.dp2 = (double*)dp2; a.dmu = (double*)dmu;
+    a.drest = (double*)drestitution; a.dA = (double*)dA; a.db = (double*)db;
+    a.wsd = (double*)h->d_bwsd.p; a.wsi = (int*)h->d_bwsi.p;
+    a.prof = h->cprof;
+    CK(bnd::launch_band_backward(a, std::min(B, h->num_sms), st));
+    return 0;
+  }
   return h->dtype == LCPB200_F32
              ? engine_backward_t<float>(h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, body1, body2,
                                         contact_count, mu, restitution, A, zhat, nu, lam, slack, dl_dzhat, dmass, dinertia, dv, dfext,

@@ -21,9 +21,9 @@ Scope (what the reference's demos use that this class mirrors): `Circle` bodies 
 `Gravity` (forces.py), `TotalConstraint` pins (constraints.py:176-192), restitution / friction as the
 mean of the two bodies (world.py:144-151, :213-224), `eps`, `tol`, `post_stab`, `strict_no_penetration`.
 Hulls (`Rect`, `Hull`), joints between bodies and the renderer are not mirrored.
-Everything is differentiable through torch autograd (the LCP through lcpb200_engine_backward) for scenes of up
-to 42 bodies (3 nb + 3 n_static <= 128); larger scenes (BASELINE config 4: a 512-ball pile) run forward-only
-in float64 through the banded large-scene kernel (csrc/lcp_banded.cuh).
+Everything is differentiable through torch autograd (the LCP through lcpb200_engine_backward). Scenes of up to
+42 bodies (3 nb + 3 n_static <= 128) use the condensed-KKT kernels (fp32 / fp64); larger scenes (BASELINE
+config 4: a 512-ball pile) the banded large-scene kernels (csrc/lcp_banded.cuh), float64.
 """
 import ctypes
 
@@ -78,7 +78,7 @@ class BatchedWorld:
         self.pi, self.pj = ii.to(self.device), jj.to(self.device)                   # pair (i, j), i < j, lexicographic
         self.cap = int(contact_capacity) if contact_capacity else min(int(self.pi.numel()), 3 * nb)
         # 3 nb + 3 n_static <= 128 and <= 256 contacts: condensed-KKT kernels (fp32 / fp64, differentiable);
-        # larger scenes: the banded large-scene kernel (fp64, forward only; lcp_banded.cuh)
+        # larger scenes: the banded large-scene kernels (fp64; lcp_banded.cuh)
         self.large = self.n + self.ne > 128 or 4 * self.cap > 1024
         if self.large and (self.dtype != torch.float64 or self.ne > 16):
             raise ValueError("BatchedWorld: scenes with 3 nb + 3 n_static > 128 (or > 256 contacts) need float64 "
