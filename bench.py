@@ -660,6 +660,30 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = t.item()
+    # the same through the same API with the gradients in FACTORED form: solve_backward(need=...) returns only
+    # dp (= dx), dh (= -dlam), db (= -dnu); dQ, dG, dF, dA are outer products of these with the forward's
+    # zhat / lam / nu (lcp.py:52-63), so a consumer that chains them further (like the engine's assembly adjoint)
+    # never needs the 0.4 MB per scene of dense gradients on the host
+    e2e_f_s = None
+    if with_bwd:
+        need_f = (False, True, False, True, False, neq > 0, False)
+        hbo_f = [hbo[k] if need_f[k] else None for k in range(7)]
+
+        def e2e_step_f():
+            solve_forward(*hin, max_iter=MAX_ITER, out=hfo, save=hsaved)
+            solve_backward(hin[0], hin[2], hin[4], hin[6], hfo[0], None, hfo[2], hfo[3], hg, need=need_f, out=hbo_f,
+                           saved=hsaved)
+
+        e2e_step_f()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step_f()
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_f_s = t.item()
     in_bytes = sum(t_.numel() * w for t_ in inp_host)
     h2d = in_bytes + (n_dof * w * B if with_bwd else 0)     # the 7 inputs once (kept on the device) + dl_dzhat
     d2h = ((n_dof + 2 * m_ineq + 1) * w + 8) * B + (in_bytes if with_bwd else 0)   # zhat, lam, slack, resid, status, iters (+ the 7 gradients)
@@ -720,6 +744,12 @@ def run_b200(args, rank, world, local_rank):
                                       "definition": "every input read once, every output written once / forward time"}},
         "clocks": clocks,
     }
+    if e2e_f_s is not None:
+        line["e2e_factored_gradients"] = {
+            "value": world * B * e2e_steps / e2e_f_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": ((n_dof + 2 * m_ineq + 1) * w + 8) * B + (n_dof + m_ineq + neq) * w * B,
+            "api": "solve_forward / solve_backward(need=(dp, dh, db)) on pinned CPU tensors: the dense dQ, dG, dF, dA are "
+                   "outer products of the returned vectors with zhat / lam / nu (lcp.py:52-63) and are not shipped"}
     if not cfg2:
         line["engine_path"] = eng
     if world == 1 and not args.no_cpu_baseline:

@@ -304,6 +304,7 @@ __device__ __noinline__ int build_structure(Ctx& c, const cnd::EngineSoA<double>
       int first = root;
       for (int sweep = 0; sweep < 2; ++sweep) {
         const int base = tail;
+        __syncwarp();
         if (lane == 0) { queue[base] = first; mark[first] = base; px[first] = 0.0; py[first] = 0.0; comp[first] = ncomp; }
         __syncwarp();
         int hd = base, tl = base + 1, lvl_end = base + 1;
@@ -321,6 +322,7 @@ __device__ __noinline__ int build_structure(Ctx& c, const cnd::EngineSoA<double>
             const unsigned same = __match_any_sync(FULL, cand ? w : -1 - lane);
             const bool win = cand && (lane == __ffs(same) - 1);
             const unsigned wb = __ballot_sync(FULL, win);
+            __syncwarp();                                                   // all reads of mark[] precede the winners' writes
             if (win) {
               const int pos = tl + __popc(wb & ((1u << lane) - 1));
               queue[pos] = w; mark[w] = pos; comp[w] = ncomp;
@@ -923,6 +925,7 @@ __device__ __forceinline__ void pass_forward(const SolveDims c, const double* bl
   for (int p = 1; p < 8; ++p)
 #pragma unroll
     for (int q = 0; q < p; ++q) y[p] = fma(-blk[p * 8 + q], y[q], y[p]);
+  __syncwarp();                                                             // every lane has read sol[k0 ..] before lane 0 overwrites it
   if (lane == 0) {
 #pragma unroll
     for (int p = 0; p < 8; ++p) c.sol[k0 + p] = y[p];
@@ -1000,6 +1003,7 @@ __device__ __forceinline__ void pass_backward(const SolveDims c, const double* b
   for (int p = 6; p >= 0; --p)
 #pragma unroll
     for (int q = p + 1; q < 8; ++q) x[p] = fma(-blk[p * 8 + q], x[q], x[p]);
+  __syncwarp();                                                             // (same: reads of sol[k0 ..] before the overwrite)
   if (lane == 0) {
 #pragma unroll
     for (int p = 0; p < 8; ++p) c.sol[k0 + p] = x[p];
