@@ -178,9 +178,8 @@ def run_reference(args, rank, world):
                           "gpu_launches": 0}), flush=True)
         return
     if args.config == "world":
-        from lcp_physics_b200.scenes import make_ball_drop
         from oracle.world_oracle import OracleCircleWorld
-        ic = make_ball_drop(1, seed=2000)
+        ic = world_initial(1, 0)
         ow = OracleCircleWorld(ic["pos"][0], ic["rad"][0], ic["vel"][0], ic["mass"][0], ic["rest"][0], ic["fric"][0],
                                gravity=100.0, static=(0,), dt=1.0 / 30)
         for _ in range(args.warmup):
@@ -193,7 +192,7 @@ def run_reference(args, rank, world):
         print(json.dumps({"impl": "reference", "metric": METRIC_WORLD, "value": val, "unit": "world-steps/s", "n_gpus": world,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": "one world (24 balls + pinned floor ball) stepped on the host"},
+                          "config": {"workload": "one world (pile of 24 balls in contact on a pinned floor ball) stepped on the host"},
                           "cpu_baseline": {"value": val, "unit": "world-steps/s", "cores": use_all_host_threads(), "kind": "port",
                                            "sample": "1 world, %d steps (oracle/world_oracle.py)" % args.steps},
                           "e2e": {"value": val, "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -267,7 +266,14 @@ def parity_sample(inp_host, g_host, fo_dev, bo_dev, n_sample, dtype, max_iter, w
 
 TOL = {torch.float32: 1e-3, torch.float64: 1e-6}
 
-METRIC_WORLD = "sim steps/sec (World.step: 24 balls dropped on a pinned floor ball, 2 fric dirs, fp64; B worlds in lock-step)"
+METRIC_WORLD = "sim steps/sec (World.step: pile of 24 balls on a pinned floor ball, 2 fric dirs, fp64; B worlds in lock-step)"
+
+
+def world_initial(B, seed):
+    """--config world: B piles of 24 balls (6 wide, hexagonal, 0.05 apart: ~55 contacts per world from step 0,
+    m ~ 220) on a pinned floor ball; every world has its own jitter."""
+    from lcp_physics_b200.scenes import make_ball_pile
+    return make_ball_pile(B, nballs=24, cols=6, seed=2000 + seed, gap=0.05)
 
 
 def run_world(args, rank, world, local_rank):
@@ -276,13 +282,12 @@ def run_world(args, rank, world, local_rank):
     (oracle/world_oracle.py, one world) on the first world of the batch, which also gives the parity figure."""
     import torch.distributed as dist
     from lcp_physics_b200 import _lib
-    from lcp_physics_b200.scenes import make_ball_drop
     from lcp_physics_b200.world import BatchedWorld
     _lib.require_cuda()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     B = args.batch or 1024
-    ic = make_ball_drop(B, seed=2000 + rank)
+    ic = world_initial(B, rank)
 
     def mk():
         return BatchedWorld(ic["pos"], ic["rad"], vel=ic["vel"], mass=ic["mass"], restitution=ic["rest"],
@@ -316,24 +321,27 @@ def run_world(args, rank, world, local_rank):
     t0 = time.perf_counter()
     w2 = BatchedWorld(hp["pos"], hp["rad"], vel=hp["vel"], mass=hp["mass"], restitution=hp["rest"], fric_coeff=hp["fric"],
                       gravity=100.0, static=[0], dt=1.0 / 30, device=dev)
+    out_p = torch.empty(B, w_.nb, 3, dtype=torch.float64).pin_memory()
     for _ in range(args.steps):
         w2.step()
-    out_p = w2.p.cpu()
+        out_p.copy_(w2.p)                                         # the step's result back to the host, every step
+    torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if rank != 0:
         return
     line = {"metric": METRIC_WORLD, "value": world * B * args.steps / (ms * 1e-3), "unit": "world-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BatchedWorld.step(): %d worlds/GPU x (24 balls + pinned floor ball), n=75, <= 75 contacts, "
+            "config": {"workload": "BatchedWorld.step(): %d worlds/GPU x (pile of 24 balls in contact + pinned floor ball), n=75, <= 75 contacts, "
                                    "fp64, max_iter=10, per-scene contact sets and dt halving" % B,
                        "global_batch": world * B, "parallelism": "world-sharded x%d" % world,
                        "mean_contacts_per_world": float(torch.stack(ncs).mean())},
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": "world-steps/s",
                     "h2d_bytes_per_step": sum(v.numel() * 8 for v in ic.values()) // max(1, args.steps),
-                    "d2h_bytes_per_step": out_p.numel() * 8 // max(1, args.steps),
-                    "api": "BatchedWorld(host tensors) -> steps -> positions back to the host"},
-            "gpu_launches": None, "clocks": clocks}
+                    "d2h_bytes_per_step": out_p.numel() * 8,
+                    "api": "BatchedWorld(pinned host tensors) once, then every step: step() + positions of all bodies "
+                           "back to pinned host memory"},
+            "gpu_launches": 2 * args.steps, "clocks": clocks}
     if world == 1 and not args.no_cpu_baseline:
         from oracle.world_oracle import OracleCircleWorld
         ow = OracleCircleWorld(ic["pos"][0], ic["rad"][0], ic["vel"][0], ic["mass"][0], ic["rest"][0], ic["fric"][0],
