@@ -620,7 +620,7 @@ __device__ __noinline__ void assemble_band(const Ctx& c) {
 // its lanes stride over the band row Kb[i][0..bw] (columns i - bw .. i) and the band column KbT[i][0..bw)
 // (rows i - bw .. i - 1), plus the 16 + 16 border entries. Loads and stores are separate steps so that a
 // pass can issue the loads before its trailing update and store after it.
-constexpr int ER = 5;               // ceil((bw + 1) / 32) for bw <= 159
+constexpr int ER = 5;               // ceil((bw + 1) / 32) for bw <= 159 (bw <= 130 here: bwa <= 128)
 struct Entering { double row[ER], col[ER], br; };
 
 __device__ __forceinline__ void enter_load(Entering& en, const double* __restrict__ Kb, const double* __restrict__ KbT,
@@ -629,6 +629,7 @@ __device__ __forceinline__ void enter_load(Entering& en, const double* __restric
   const bool ent = i < Nbp;
 #pragma unroll
   for (int q = 0; q < ER; ++q) {
+    if (32 * q > bw) break;                                                 // (warp-uniform: rounds beyond the band are skipped)
     const int u = lane + 32 * q;
     en.row[q] = (ent && u <= bw) ? Kb[(size_t)i * ldk + u] : 0.0;
     en.col[q] = (ent && u < bw) ? KbT[(size_t)i * ldk + u] : 0.0;
@@ -644,6 +645,7 @@ __device__ __forceinline__ void enter_store(const Entering& en, double* win, int
   if (js0 >= Wc) js0 -= Wc;
 #pragma unroll
   for (int q = 0; q < ER; ++q) {
+    if (32 * q > bw) break;
     const int u = lane + 32 * q;
     int sj = js0 + u;
     if (sj >= Wc) sj -= Wc;

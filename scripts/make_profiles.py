@@ -65,7 +65,7 @@ def main():
         d, u = raw(rep)
         with open('profiles/%s_%s_ncu_summary.txt' % (tag, name), 'w') as f:
             f.write('# ncu --set full (+ local-memory / fp64-pipe counters) --clock-control none --import-source on, one launch of\n')
-            f.write('# kernel: %s   (B = %s scenes, %s; python scripts/prof_target.py)\n' % (d.get('Kernel Name'), batch, cfg))
+            f.write('# kernel: %s   (B = %s scenes, %s; python scripts/%s)\n' % (d.get('Kernel Name'), batch, cfg, 'band_target.py' if cfg == 'cfg4' else 'prof_target.py'))
             for k in KEYS:
                 if k in d:
                     f.write('%-72s %s %s\n' % (k, d[k], u.get(k, '')))
