@@ -93,9 +93,33 @@ def scene_chain():
     return World(bodies, joints, dt=1.0 / 30, engine=RecordingEngine, post_stab=False)
 
 
+def scene_large():
+    """60 circles (radius 10, hexagonal pile 10 wide, 0.05 apart) resting on a Rect floor: 183 dofs, ~150 contacts
+    (m ~ 600) -- too large for the condensed-KKT kernels, B200PdipmEngine routes it to the banded kernel
+    (csrc/lcp_banded.cuh); post_stab=True records both engine modes. The floor touches a whole row of balls."""
+    import math
+    bodies, joints = [], []
+    floor = Rect([300, 480], [700, 20])
+    bodies.append(floor)
+    joints.append(TotalConstraint(floor))
+    pitch = 20.05
+    for k in range(60):
+        row, col = divmod(k, 10)
+        x = 300 + pitch * (col - 4.5) + (row % 2) * pitch / 2
+        y = 470 - 10 - 0.05 - row * pitch * math.sqrt(3) / 2
+        c = Circle([x, y], 10, restitution=0.4, fric_coeff=0.6)
+        c.add_force(Gravity(g=100))
+        bodies.append(c)
+    return World(bodies, joints, dt=1.0 / 30, engine=RecordingEngine, post_stab=True)
+
+
 def main():
     torch.manual_seed(0)
-    for name, builder, steps in (("world_pile", scene_pile, 25), ("world_chain", scene_chain, 25)):
+    which = sys.argv[1:] or ["world_pile", "world_chain", "world_large"]
+    for name, builder, steps in (("world_pile", scene_pile, 25), ("world_chain", scene_chain, 25),
+                                 ("world_large", scene_large, 8)):
+        if name not in which:
+            continue
         RecordingEngine.records = []
         world = builder()
         for _ in range(steps):

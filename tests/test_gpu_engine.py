@@ -11,12 +11,14 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("fused", [True, False])
-@pytest.mark.parametrize("name", ["world_pile", "world_chain"])
+@pytest.mark.parametrize("name", ["world_pile", "world_chain", "world_large"])
 def test_engine_replays_reference_world(name, fused):
-    """fused=True: lcpb200_engine_forward (contact list -> solution, nothing dense); False: GPU assembly + LCPFunction."""
+    """fused=True: lcpb200_engine_forward (contact list -> solution, nothing dense); False: GPU assembly + LCPFunction.
+    world_large (60 circles on a Rect floor, 183 dofs, up to 159 contacts; solve_dynamics and post_stabilization
+    calls): fused = the banded large-scene kernel, not fused = the dual-form kernels' L2 plan."""
     from lcp_physics_b200.engines import B200PdipmEngine
     recs = load_world_records(name)
-    assert len(recs) >= 20
+    assert len(recs) >= 16
     worst = 0.0
     for rec in recs:
         world = ReplayWorld(rec)
