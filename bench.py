@@ -603,11 +603,12 @@ def run_b200(args, rank, world, local_rank):
         if record:
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record()
-        solve_forward(Q, p, G, h, A, b, F, max_iter=MAX_ITER, out=fo)
+        saved = {}
+        solve_forward(Q, p, G, h, A, b, F, max_iter=MAX_ITER, out=fo, save=saved)
         if record:
             e1.record()
         if with_bwd:
-            solve_backward(Q, G, A, F, fo[0], None, fo[2], fo[3], g, out=bo)
+            solve_backward(Q, G, A, F, fo[0], None, fo[2], fo[3], g, out=bo, saved=saved)   # as LCPFunction.backward does
         if record:
             e2.record()
             kev.append((e0, e1, e2))

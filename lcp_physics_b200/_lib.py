@@ -96,6 +96,7 @@ class Handle:
         check(lib.lcpb200_create(dtype_code(dtype), n, m, e, device_index, ctypes.byref(self._h)))
         self.key = (dtype, n, m, e, device_index)
         self.host_generation = 0        # bumped by every host-buffer call (retained-state token)
+        self.fwd_generation = 0         # bumped by every device forward (structure-reuse token, lcp.py)
 
     def describe(self):
         buf = ctypes.create_string_buffer(512)

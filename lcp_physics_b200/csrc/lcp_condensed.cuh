@@ -58,6 +58,7 @@ struct CPlan {
   int smem_bytes;
   int ctas_per_sm;
   int flags;                  // experiment switches (LCPB200_COND_FLAGS): 1 = 1/d in fp64, 2 = rz - rs/d in fp64
+  int sbytes;                 // bytes of one scene's saved structure (save_structure / load_structure)
   // byte offsets into the dynamic shared memory (filled by carve_plan)
   int o_K, o_W, o_scr, o_bx, o_rdiag, o_Fd, o_Gd, o_As, o_x, o_rx, o_dx, o_qd, o_y, o_ry, o_dy,
       o_s, o_z, o_d, o_rz, o_ds, o_dz, o_rs2, o_red, o_rows, o_posof, o_clist, o_ccols, o_ncols, o_clcnt, o_misc;
@@ -101,6 +102,8 @@ inline size_t carve_plan(CPlan& P, int tsize) {
   CND_TAKE(o_clcnt, n);
   CND_TAKE(o_misc, 16 * 4);
 #undef CND_TAKE
+  // what build_structure leaves behind: {Struct} + [Fd, Gd, As] + [qd] + [rows, posof, clist, ccols, ncols, clcnt]
+  P.sbytes = 16 + (P.o_x - P.o_Fd) + (P.o_y - P.o_qd) + (P.o_misc - P.o_rows);
   return o;
 }
 
@@ -1030,6 +1033,7 @@ struct CFwdArgs {
   int not_improved_lim, max_iter;
   long long* prof;            // nullptr or [grid][CPH_COUNT]
   EngineSoA<T> soa;           // soa.mass != nullptr: structure, p and h come from the contact list (Q, G, F unused)
+  unsigned char* ssave;       // nullptr or [B][P.sbytes]: the structure found for every scene, kept for the backward
 };
 
 template <typename T>
@@ -1042,10 +1046,42 @@ struct CBwdArgs {
   int* done;                  // nullptr or [B]: 1 = gradients written here, 0 = scene left to the dual-form kernel
   const int* only;            // nullptr or [B]: process only the scenes flagged non-zero (rescue pass after the dual form)
   unsigned flags;             // LCPB200_BWD_*: bit 0 = exact adjoint (transposed KKT system: K^T, W^T)
+  const unsigned char* sload; // nullptr or [B][P.sbytes]: structure saved by the forward of the SAME inputs (skips the scan of Q, G, F)
   EngineSoA<T> soa;           // engine path: gradients w.r.t. the contact list instead of dense ones
   T *dmass, *dinertia, *dv, *dfext, *dnormal, *dp1, *dp2, *dmu, *drest;   // engine path outputs (any may be nullptr)
   long long* prof;
 };
+
+// ------------------------------------------------------------------ structure save / reuse
+// The backward of a scene needs the same structure as its forward (components of F, block forms of G and F,
+// column lists): 19 KB at cfg 3 against the 0.4 MB of dense Q, G, F it would have to scan again. The forward
+// writes it to a per-scene slot of the handle's buffer, the backward of the same inputs reads it back.
+__device__ __forceinline__ void copy16(unsigned char* dst, const unsigned char* src, int bytes) {
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  for (int i = threadIdx.x; i < (bytes >> 4); i += NT) d4[i] = s4[i];
+}
+
+__device__ __forceinline__ void save_structure(const CPlan& P, const Struct& st, bool ok, unsigned char* dst) {
+  if (threadIdx.x == 0) *reinterpret_cast<int4*>(dst) = make_int4(ok ? st.ncomp : -1, st.cs, st.sh, st.m);
+  if (!ok) return;
+  const int c1 = P.o_x - P.o_Fd, c2 = P.o_y - P.o_qd, c3 = P.o_misc - P.o_rows;
+  copy16(dst + 16, cnd_smem + P.o_Fd, c1);
+  copy16(dst + 16 + c1, cnd_smem + P.o_qd, c2);
+  copy16(dst + 16 + c1 + c2, cnd_smem + P.o_rows, c3);
+}
+
+// returns false when the forward found no structure for this scene (it went to the dual-form kernel)
+__device__ __forceinline__ bool load_structure(const CPlan& P, Struct& st, const unsigned char* src) {
+  const int4 hd = *reinterpret_cast<const int4*>(src);
+  st.ncomp = hd.x; st.cs = hd.y; st.sh = hd.z; st.m = hd.w;
+  if (hd.x < 0) return false;
+  const int c1 = P.o_x - P.o_Fd, c2 = P.o_y - P.o_qd, c3 = P.o_misc - P.o_rows;
+  copy16(cnd_smem + P.o_Fd, src + 16, c1);
+  copy16(cnd_smem + P.o_qd, src + 16 + c1, c2);
+  copy16(cnd_smem + P.o_rows, src + 16 + c1 + c2, c3);
+  return true;
+}
 
 // ------------------------------------------------------------------ forward (pdipm.py:49-179), one scene
 template <typename T, int NS, int CS>
@@ -1212,6 +1248,7 @@ __global__ void __launch_bounds__(NT, (NS <= 6) ? 2 : 1) cond_forward_kernel(con
         : build_structure<T>(P, S, st, a.Q + (size_t)sc * n * n, a.G + (size_t)sc * m * n,
                              e > 0 ? a.A + (size_t)sc * e * n : nullptr, a.F + (size_t)sc * m * m, &singular_s);
     __syncthreads();
+    if (a.ssave) save_structure(P, st, ok, a.ssave + (size_t)sc * P.sbytes);
     pf.lap(CPH_STRUCT);
     if (!ok) {
       if (singular_s) {                 // pdipm.py:361-368: the caller raises
@@ -1234,6 +1271,42 @@ __global__ void __launch_bounds__(NT, (NS <= 6) ? 2 : 1) cond_forward_kernel(con
       default: forward_scene<T, NS, 6>(a, S, st, pf, sc); break;
     }
     __syncthreads();
+  }
+}
+
+// o[i][j] = f(i, j), row-major rows x cols, written by the whole CTA. When a row is a multiple of 16 bytes and o is
+// 16-byte aligned a thread produces V = 16 / sizeof(T) consecutive elements of one row and stores them at once
+// (the scalar form spent 26 % of the backward kernel's instructions on index bookkeeping and 4-byte stores).
+template <typename T, typename F>
+__device__ __forceinline__ void write_outer(T* __restrict__ o, int rows, int cols, F f) {
+  constexpr int V = 16 / (int)sizeof(T);
+  const int tid = threadIdx.x;
+  if (cols % V == 0 && (reinterpret_cast<size_t>(o) & 15) == 0) {
+    const int cv = cols / V, total = rows * cv;
+    const int di = NT / cv, dj = NT - di * cv;
+    int i = tid / cv, jv = tid - i * cv;
+    for (int t = tid; t < total; t += NT) {
+      const int j = jv * V;
+      if (V == 4) {
+        float4 w;
+        w.x = (float)f(i, j); w.y = (float)f(i, j + 1); w.z = (float)f(i, j + 2); w.w = (float)f(i, j + 3);
+        reinterpret_cast<float4*>(o)[t] = w;
+      } else {
+        double2 w;
+        w.x = (double)f(i, j); w.y = (double)f(i, j + 1);
+        reinterpret_cast<double2*>(o)[t] = w;
+      }
+      i += di; jv += dj;
+      if (jv >= cv) { jv -= cv; ++i; }
+    }
+  } else {
+    int i = tid / cols, j = tid - i * cols;
+    const int di = NT / cols, dj = NT - di * cols;
+    for (size_t t = tid; t < (size_t)rows * cols; t += NT) {
+      o[t] = f(i, j);
+      i += di; j += dj;
+      if (j >= cols) { j -= cols; ++i; }
+    }
   }
 }
 
@@ -1362,50 +1435,15 @@ __device__ __forceinline__ void backward_scene(const CBwdArgs<T>& a, CSmem<T>& S
   if (a.dp) for (int i = tid; i < n; i += NT) a.dp[(size_t)sc * n + i] = dx[i];                       // :52
   if (a.dh) for (int i = tid; i < m; i += NT) a.dh[(size_t)sc * m + i] = -dlam[i];                    // :55
   if (a.db && e > 0) for (int i = tid; i < e; i += NT) a.db[(size_t)sc * e + i] = -dnu[i];            // :58
-  if (a.dG) {                                                    // :53  dlam (x) zhat + lam (x) dx
-    T* o = a.dG + (size_t)sc * m * n;
-    { int i = 0, j = tid;
-      while (j >= n) { j -= n; ++i; }
-      for (size_t t = tid; t < (size_t)m * n; t += NT) {
-        o[t] = dlam[i] * S.x()[j] + S.z()[i] * dx[j];
-        j += NT;
-        while (j >= n) { j -= n; ++i; }
-      }
-    }
-  }
-  if (a.dF) {                                                    // :54  -dlam (x) lam
-    T* o = a.dF + (size_t)sc * m * m;
-    { int i = 0, j = tid;
-      while (j >= m) { j -= m; ++i; }
-      for (size_t t = tid; t < (size_t)m * m; t += NT) {
-        o[t] = -(dlam[i] * S.z()[j]);
-        j += NT;
-        while (j >= m) { j -= m; ++i; }
-      }
-    }
-  }
-  if (a.dA && e > 0) {                                           // :57
-    T* o = a.dA + (size_t)sc * e * n;
-    { int i = 0, j = tid;
-      while (j >= n) { j -= n; ++i; }
-      for (size_t t = tid; t < (size_t)e * n; t += NT) {
-        o[t] = dnu[i] * S.x()[j] + S.y()[i] * dx[j];
-        j += NT;
-        while (j >= n) { j -= n; ++i; }
-      }
-    }
-  }
-  if (a.dQ) {                                                    // :61
-    T* o = a.dQ + (size_t)sc * n * n;
-    { int i = 0, j = tid;
-      while (j >= n) { j -= n; ++i; }
-      for (size_t t = tid; t < (size_t)n * n; t += NT) {
-        o[t] = T(0.5) * (dx[i] * S.x()[j] + S.x()[i] * dx[j]);
-        j += NT;
-        while (j >= n) { j -= n; ++i; }
-      }
-    }
-  }
+  // the four dense outer products (0.4 MB per scene at cfg 3): 16-byte stores, V elements of one row per thread
+  if (a.dG)                                                      // :53  dlam (x) zhat + lam (x) dx
+    write_outer<T>(a.dG + (size_t)sc * m * n, m, n, [&](int i, int j) { return dlam[i] * S.x()[j] + S.z()[i] * dx[j]; });
+  if (a.dF)                                                      // :54  -dlam (x) lam
+    write_outer<T>(a.dF + (size_t)sc * m * m, m, m, [&](int i, int j) { return -(dlam[i] * S.z()[j]); });
+  if (a.dA && e > 0)                                             // :57
+    write_outer<T>(a.dA + (size_t)sc * e * n, e, n, [&](int i, int j) { return dnu[i] * S.x()[j] + S.y()[i] * dx[j]; });
+  if (a.dQ)                                                      // :61
+    write_outer<T>(a.dQ + (size_t)sc * n * n, n, n, [&](int i, int j) { return T(0.5) * (dx[i] * S.x()[j] + S.x()[i] * dx[j]); });
   if (tid == 0 && a.done) a.done[sc] = 1;
   __syncthreads();
   pf.lap(CPH_GRADS);
@@ -1427,8 +1465,10 @@ __global__ void __launch_bounds__(NT, (NS <= 6) ? 2 : 1) cond_backward_kernel(co
     Struct st;
     const bool ok = a.soa.mass
         ? build_structure_soa<T>(P, S, st, a.soa, sc, e > 0 ? a.A + (size_t)sc * e * n : nullptr, &singular_s)
-        : build_structure<T>(P, S, st, a.Q + (size_t)sc * n * n, a.G + (size_t)sc * m * n,
-                             e > 0 ? a.A + (size_t)sc * e * n : nullptr, a.F + (size_t)sc * m * m, &singular_s);
+        : a.sload
+              ? load_structure(P, st, a.sload + (size_t)sc * P.sbytes)       // the forward of the same inputs found it
+              : build_structure<T>(P, S, st, a.Q + (size_t)sc * n * n, a.G + (size_t)sc * m * n,
+                                   e > 0 ? a.A + (size_t)sc * e * n : nullptr, a.F + (size_t)sc * m * m, &singular_s);
     __syncthreads();
     pf.lap(CPH_STRUCT);
     if (!ok) {

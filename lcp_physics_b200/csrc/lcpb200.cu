@@ -77,6 +77,8 @@ struct lcpb200_handle_s {
   DevBuf d_in[7], d_out[6], d_bwd[16];
   long long* prof = nullptr;      // optional per-CTA phase cycle counters [NSLOT*max_grid][PH_COUNT]
   long long* cprof = nullptr;     // same for the condensed kernels [NSLOT*cond_grid][CPH_COUNT]
+  DevBuf d_struct;                // [struct_B][cplan.sbytes]: structure of every scene of the last lcpb200_forward
+  int struct_B = 0;               // ... and its batch size (0 = nothing saved)
   DevBuf d_R;                     // host pipeline: R of every scene, kept for backward_host
   int retained_B = 0;             // scenes whose inputs/results forward_host left on the device
   bool retained_R = false;        // ... and whether R of those scenes is in d_R
@@ -274,6 +276,7 @@ extern "C" int lcpb200_destroy(lcpb200_handle_t h) {
   DeviceGuard dg_;
   dg_.set(h->device);
   if (h->ws) cudaFree(h->ws);
+  h->d_struct.release();
   if (h->prof) cudaFree(h->prof);
   if (h->cprof) cudaFree(h->cprof);
   for (auto& s : h->streams) if (s) cudaStreamDestroy(s);
@@ -316,7 +319,8 @@ template <typename T>
 static int launch_forward(lcpb200_handle_s* h, int slot, int B, const void* Q, const void* p, const void* G,
                           const void* hv, const void* A, const void* b, const void* F, double eps,
                           int not_improved_lim, int max_iter, void* zhat, void* nu, void* lam, void* slack,
-                          int32_t* status, int32_t* iters, void* resid, void* Rsave, cudaStream_t st) {
+                          int32_t* status, int32_t* iters, void* resid, void* Rsave, cudaStream_t st,
+                          unsigned char* ssave = nullptr) {
   const bool cond = h->cplan.ok != 0;
   if (cond) {
     // structured scenes: condensed-KKT kernel; it flags the others (status = -100) for the dual-form kernel below
@@ -329,6 +333,7 @@ static int launch_forward(lcpb200_handle_s* h, int slot, int B, const void* Q, c
     c.status = status; c.iters = iters;
     c.eps = (T)eps; c.not_improved_lim = not_improved_lim; c.max_iter = max_iter;
     memset(&c.soa, 0, sizeof(c.soa));
+    c.ssave = ssave;
     c.prof = h->cprof ? h->cprof + (size_t)slot * h->cond_grid * cnd::CPH_COUNT : nullptr;
     const int cgrid = std::min(B, h->cond_grid);
 #define CALL_FWD(NSV) cnd::launch_cond_forward_t<T, NSV>(c, cgrid, st)
@@ -363,7 +368,7 @@ template <typename T>
 static int launch_backward(lcpb200_handle_s* h, int slot, int B, const void* Q, const void* G, const void* A,
                            const void* F, const void* zhat, const void* nu, const void* lam, const void* slack,
                            const void* g, void* dQ, void* dp, void* dG, void* dh, void* dA, void* db, void* dF,
-                           const void* Rsave, unsigned flags, cudaStream_t st) {
+                           const void* Rsave, unsigned flags, cudaStream_t st, const unsigned char* sload = nullptr) {
   // fp32: condensed-KKT backward first, the dual form only for the scenes it flags as unstructured.
   // fp64: the dual form first -- at the fp64 round-off floor (lambda, s ~ 1e-16, d = lambda/s spanning
   // 1e+-16) the condensed matrix loses dx (DESIGN.md "Parity") -- and the condensed kernel only as a rescue
@@ -386,6 +391,7 @@ static int launch_backward(lcpb200_handle_s* h, int slot, int B, const void* Q, 
     c.done = cond_first ? flagbuf : nullptr;
     c.only = cond_first ? nullptr : flagbuf;
     c.flags = flags;
+    c.sload = sload;
     memset(&c.soa, 0, sizeof(c.soa));
     c.dmass = c.dinertia = c.dv = c.dfext = c.dnormal = c.dp1 = c.dp2 = c.dmu = c.drest = nullptr;
     c.prof = h->cprof ? h->cprof + (size_t)slot * h->cond_grid * cnd::CPH_COUNT : nullptr;
@@ -450,11 +456,21 @@ extern "C" int lcpb200_forward(lcpb200_handle_t h, int B, const void* Q, const v
   DeviceGuard dg_;
   CK(dg_.set(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  return h->dtype == LCPB200_F32
+  // the structure of every scene is kept for a backward of the same inputs (LCPB200_BWD_REUSE_STRUCTURE)
+  unsigned char* ssave = nullptr;
+  h->struct_B = 0;
+  if (h->cplan.ok) {
+    if ((size_t)B * h->cplan.sbytes > h->d_struct.bytes) CK(cudaDeviceSynchronize());    // (an earlier launch may still read it)
+    CK(h->d_struct.ensure((size_t)B * h->cplan.sbytes));
+    ssave = (unsigned char*)h->d_struct.p;
+  }
+  const int rc = h->dtype == LCPB200_F32
              ? launch_forward<float>(h, 0, B, Q, p, G, hv, A, b, F, eps, not_improved_lim, max_iter, zhat, nu, lam,
-                                     slack, status, iters, resid, Rsave, st)
+                                     slack, status, iters, resid, Rsave, st, ssave)
              : launch_forward<double>(h, 0, B, Q, p, G, hv, A, b, F, eps, not_improved_lim, max_iter, zhat, nu, lam,
-                                      slack, status, iters, resid, Rsave, st);
+                                      slack, status, iters, resid, Rsave, st, ssave);
+  if (rc == 0 && ssave) h->struct_B = B;
+  return rc;
 }
 
 extern "C" int lcpb200_backward(lcpb200_handle_t h, int B, const void* Q, const void* G, const void* A,
@@ -466,15 +482,20 @@ extern "C" int lcpb200_backward(lcpb200_handle_t h, int B, const void* Q, const 
   if (B < 0) return fail("B < 0");
   if (!Q || !G || !F || !zhat || !lam || !slack || !g) return fail("Q, G, F, zhat, lam, slack, dl_dzhat must be non-NULL");
   if (h->e > 0 && (!A || !nu)) return fail("A and nu must be non-NULL when e > 0");
-  if (flags != LCPB200_BWD_BUG_COMPATIBLE && flags != LCPB200_BWD_EXACT_ADJOINT)
-    return fail("flags must be LCPB200_BWD_BUG_COMPATIBLE or LCPB200_BWD_EXACT_ADJOINT");
+  if (flags & ~(LCPB200_BWD_EXACT_ADJOINT | LCPB200_BWD_REUSE_STRUCTURE))
+    return fail("flags: LCPB200_BWD_EXACT_ADJOINT | LCPB200_BWD_REUSE_STRUCTURE are the defined bits");
   if (B == 0) return 0;
   DeviceGuard dg_;
   CK(dg_.set(h->device));
   cudaStream_t st = (cudaStream_t)stream;
+  // LCPB200_BWD_REUSE_STRUCTURE: the caller states that (Q, G, A, F) are the inputs of the last lcpb200_forward on
+  // this handle; ignored when nothing (or another batch size) was saved
+  const unsigned char* sload = ((flags & LCPB200_BWD_REUSE_STRUCTURE) && h->cplan.ok && h->struct_B == B)
+                                   ? (const unsigned char*)h->d_struct.p : nullptr;
+  const unsigned kf = flags & LCPB200_BWD_EXACT_ADJOINT;
   return h->dtype == LCPB200_F32
-             ? launch_backward<float>(h, 0, B, Q, G, A, F, zhat, nu, lam, slack, g, dQ, dp, dG, dh, dA, db, dF, Rsave, flags, st)
-             : launch_backward<double>(h, 0, B, Q, G, A, F, zhat, nu, lam, slack, g, dQ, dp, dG, dh, dA, db, dF, Rsave, flags, st);
+             ? launch_backward<float>(h, 0, B, Q, G, A, F, zhat, nu, lam, slack, g, dQ, dp, dG, dh, dA, db, dF, Rsave, kf, st, sload)
+             : launch_backward<double>(h, 0, B, Q, G, A, F, zhat, nu, lam, slack, g, dQ, dp, dG, dh, dA, db, dF, Rsave, kf, st, sload);
 }
 
 extern "C" int lcpb200_profile(lcpb200_handle_t h, int enable, long long* out) {
@@ -736,6 +757,7 @@ static int engine_forward_t(lcpb200_handle_s* h, int B, int nb, int nc, int mode
   c.Q = nullptr; c.G = nullptr; c.F = nullptr;
   c.A = (const T*)A; c.b = (const T*)b;
   fill_soa<T>(c.soa, h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, b1, b2, mu, rest, ncs);
+  c.ssave = nullptr;
   c.p = c.soa.p_s; c.h = c.soa.h_s;
   c.zhat = (T*)zhat; c.nu = (T*)nu; c.lam = (T*)lam; c.slack = (T*)slack; c.resid = (T*)resid;
   c.status = status; c.iters = iters;
@@ -810,7 +832,7 @@ static int engine_backward_t(lcpb200_handle_s* h, int B, int nb, int nc, int mod
   c.zhat = (const T*)zhat; c.nu = (const T*)nu; c.lam = (const T*)lam; c.slack = (const T*)slack; c.g = (const T*)g;
   c.dQ = c.dp = c.dG = c.dh = c.dF = nullptr;
   c.dA = (T*)dA; c.db = (T*)db;
-  c.done = nullptr; c.only = nullptr; c.flags = flags;
+  c.done = nullptr; c.only = nullptr; c.flags = flags; c.sload = nullptr;
   c.prof = h->cprof;
   fill_soa<T>(c.soa, h, B, nb, nc, mode, dt, mass, inertia, v, fext, normal, p1, p2, b1, b2, mu, rest, ncs);
   c.dmass = (T*)dmass; c.dinertia = (T*)dinertia; c.dv = (T*)dv; c.dfext = (T*)dfext; c.dnormal = (T*)dnormal;

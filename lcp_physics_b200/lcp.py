@@ -98,8 +98,13 @@ def solve_forward(Q, p, G, h, A, b, F, eps=1e-12, not_improved_lim=3, max_iter=1
         if save is not None:
             save["token"] = (hd, hd.host_generation, B)
     else:
+        hd.fwd_generation += 1
         with torch.cuda.device(dev):
             _lib.check(lib.lcpb200_forward(*args, None, _stream_ptr(dev)))
+        if save is not None:
+            # the library keeps the block structure it found for these inputs; a backward for the SAME inputs
+            # may reuse it as long as no other forward ran on this handle in between (LCPB200_BWD_REUSE_STRUCTURE)
+            save["struct"] = (hd, hd.fwd_generation, B)
     return zhat, nu, lam, slack, status, iters, resid
 
 
@@ -107,7 +112,8 @@ def solve_backward(Q, G, A, F, zhat, nu, lam, slack, dl_dzhat, need=(True,) * 7,
                    exact_adjoint=False):
     """Raw backward (lcp.py:37-64): returns (dQ, dp, dG, dh, dA, db, dF); entries
     not needed (or dA/db when e == 0) are None. `out`: preallocated results.
-    `saved`: the dict filled by solve_forward(save=...) for the same inputs.
+    `saved`: the dict filled by solve_forward(save=...) for the same inputs (host path: the state retained on
+    the device; CUDA path: a token that lets the backward reuse the block structure the forward found).
     `exact_adjoint`: False = the reference's behaviour (it re-uses the UN-transposed KKT
     factorisation, which is the true adjoint only when F == 0 -- SURVEY.md F6); True = the
     transposed system (F^T in place of F inside the KKT solve), the exact gradient."""
@@ -143,7 +149,10 @@ def solve_backward(Q, G, A, F, zhat, nu, lam, slack, dl_dzhat, need=(True,) * 7,
         hd.host_generation += 1
         _lib.check(lib.lcpb200_backward_host(hd.raw, B, *in_ptrs, *[_lib.ptr(t) for t in outs], 1 if exact_adjoint else 0))
     else:
-        args = [hd.raw, B] + [_lib.ptr(t) for t in ins] + [_lib.ptr(t) for t in outs] + [None, 1 if exact_adjoint else 0]
+        tok = saved.get("struct") if saved else None
+        reuse = tok is not None and tok[0] is hd and tok[1] == hd.fwd_generation and tok[2] == B
+        flags = (1 if exact_adjoint else 0) | (2 if reuse else 0)
+        args = [hd.raw, B] + [_lib.ptr(t) for t in ins] + [_lib.ptr(t) for t in outs] + [None, flags]
         with torch.cuda.device(dev):
             _lib.check(lib.lcpb200_backward(*args, _stream_ptr(dev)))
     return tuple(outs)

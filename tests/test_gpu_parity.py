@@ -521,3 +521,36 @@ def test_full_size_cfg2_fp64_sample_matches_oracle():
     sub = tuple(t[idx] if t.dim() > 1 else t for t in inp)
     ref = po.lcp_forward(*sub, max_iter=10, coupled=False)
     assert rel_err(out[0].cpu()[idx], ref.zhat).max() < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_backward_with_reused_structure_is_bitwise_the_same(dtype):
+    """LCPB200_BWD_REUSE_STRUCTURE: the backward that reads the block structure its forward saved (19 KB per scene
+    at cfg 3) returns bit-for-bit the gradients of the backward that scans Q, G, F again -- also when some scenes of
+    the batch have no structure (dense F / dense G row / non-diagonal Q: left to the dual form) and when another
+    forward on the same handle invalidates the token (falls back to scanning)."""
+    from lcp_physics_b200 import solve_forward, solve_backward
+    from lcp_physics_b200.scenes import make_scenes
+    inp = [t.clone() for t in make_scenes(24, 32, 64, fd=2, e=0, dtype=torch.float64, seed=31)]
+    Q, p, G, h, A, b, F = inp
+    gen = torch.Generator().manual_seed(7)
+    W = torch.randn(256, 256, generator=gen, dtype=torch.float64) * 0.02
+    F[2] += W @ W.t()
+    Q[9, 0, 1] = Q[9, 1, 0] = 0.05
+    dev = _cuda([t.to(dtype) for t in inp])
+    g = torch.randn(24, 96, generator=gen, dtype=torch.float64).to(dtype).cuda()
+    saved = {}
+    out = solve_forward(*dev, max_iter=10, save=saved)
+    assert "struct" in saved
+    reused = solve_backward(dev[0], dev[2], None, dev[6], out[0], None, out[2], out[3], g, saved=saved)
+    scanned = solve_backward(dev[0], dev[2], None, dev[6], out[0], None, out[2], out[3], g)
+    for name, a, c in zip(GRADS, reused, scanned):
+        if a is not None:
+            assert torch.equal(a, c), name
+    # a second forward (other inputs, same shapes) on the handle: the old token must not be honoured
+    other = _cuda([t.to(dtype) for t in make_scenes(24, 32, 64, fd=2, e=0, dtype=torch.float64, seed=32)])
+    solve_forward(*other, max_iter=10, save={})
+    stale = solve_backward(dev[0], dev[2], None, dev[6], out[0], None, out[2], out[3], g, saved=saved)
+    for name, a, c in zip(GRADS, stale, scanned):
+        if a is not None:
+            assert torch.equal(a, c), name
