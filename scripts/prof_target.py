@@ -13,9 +13,10 @@ if cfg == "cfg3":
 else:
     inp = [t.cuda() for t in make_scenes(B, 16, 32, fd=3, e=0, dtype=torch.float64, seed=7)]
 for rep in range(2):
-    out = solve_forward(*inp, max_iter=10)
+    saved = {}
+    out = solve_forward(*inp, max_iter=10, save=saved)
     if bwd:
         g = torch.randn_like(out[0])
-        solve_backward(inp[0], inp[2], None, inp[6], out[0], None, out[2], out[3], g)
+        solve_backward(inp[0], inp[2], None, inp[6], out[0], None, out[2], out[3], g, saved=saved)   # as LCPFunction does
 torch.cuda.synchronize()
 print("ok", out[4].unique().tolist())
