@@ -62,13 +62,34 @@ def _stale(obj, digest):
         return f.read().strip() != digest
 
 
+STAMP = LIB + ".sha"      # digest of every source + flag the library was built from (git-ignored, travels with the .so)
+
+
+def _lib_digest():
+    h = hashlib.sha256()
+    for obj, _, defs, deps in _jobs():
+        h.update((obj + ":" + _digest(deps, defs)).encode())
+    return h.hexdigest()
+
+
 def is_fresh():
+    """True when liblcpb200.so was built from the current sources and flags -- also on a box that received the
+    library without the object directory (gpurun ships *.so, not csrc/build/)."""
     if not os.path.exists(LIB):
         return False
+    if os.path.exists(STAMP):
+        with open(STAMP) as f:
+            if f.read().strip() == _lib_digest():
+                return True
     return not any(_stale(obj, _digest(deps, defs)) for obj, _, defs, deps in _jobs())
 
 
 def build(force=False, verbose=True, max_parallel=None):
+    if not force and is_fresh():
+        if not os.path.exists(STAMP):
+            with open(STAMP, "w") as f:
+                f.write(_lib_digest())
+        return LIB
     os.makedirs(OBJDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     todo = []
@@ -117,6 +138,8 @@ def build(force=False, verbose=True, max_parallel=None):
     if verbose:
         print("[lcp_physics_b200.build]", " ".join(link), flush=True)
     subprocess.check_call(link, cwd=CSRC)
+    with open(STAMP, "w") as f:
+        f.write(_lib_digest())
     return LIB
 
 
