@@ -193,9 +193,13 @@ int lcpb200_assemble_backward(int dtype, int B, int nb, int nc, double dt,
  *           zhat = LCP(M, 0, Jc, (Jc v)(1 - rest), A, b, 0).
  * Inputs are the contact structure-of-arrays of lcpb200_assemble (+ optional equality rows A[B,e,n], b[B,e],
  * e.g. World.Je()); nothing dense is written to or read from HBM. The handle must have been created with
- * n = 3 nb, m = 4 nc (mode 0) or nc (mode 1), and n + e <= 128 (the condensed-KKT kernels). A scene whose
- * contact topology the kernel cannot take (a contact of a body with itself, > 16 contact rows per degree of
- * freedom) gets status -100 and no result: assemble it with lcpb200_assemble and call lcpb200_forward.
+ * n = 3 nb, m = 4 nc (mode 0) or nc (mode 1). n + e <= 128: the condensed-KKT kernels (fp32 / fp64); larger
+ * scenes (fp64 only, e.g. BASELINE config 4: 512 bodies): the banded large-scene kernels (lcp_banded.cuh), which
+ * order the bodies so that the condensed matrix is an arrow matrix (half bandwidth <= 128 after the ordering, <= 16
+ * border rows: pinned bodies, bodies with > 12 contacts, equality rows). A scene whose contact topology the kernel
+ * cannot take (a contact of a body with itself, > 16 contacts on one body for the condensed kernels, a band or
+ * border beyond the limits above) gets status -100 and no result: assemble it with lcpb200_assemble and call
+ * lcpb200_forward.
  * contact_count == NULL: every scene has the nc contacts body1[nc], body2[nc] (one topology for the batch).
  * contact_count[B] != NULL (batched worlds): scene s uses its first contact_count[s] <= nc contacts, body1 /
  * body2 are [B,nc] and all per-contact arrays are strided by nc; a scene with 0 contacts gets the
