@@ -156,6 +156,16 @@ int lcpb200_backward_host(lcpb200_handle_t h, int B,
 int lcpb200_find_contacts(int dtype, int B, int nb, int cap, double eps, const void* pos, const void* rad,
                           int32_t* body1, int32_t* body2, int32_t* counts, void* stream);
 
+/* Geometry and material of the pairs selected by lcpb200_find_contacts (contacts.py:69-77, world.py:144-151,
+ * :213-224), for callers that do not differentiate through the contact generation:
+ *   normal[B,cap,2] = (pos1 - pos2) / dist, penetration[B,cap] = r1 + r2 - dist (-1e30 in unused slots),
+ *   p1 = -normal (r1 - pen / 2), p2 = normal (r2 - pen / 2), mu / restitution[B,cap] = mean of the two bodies'
+ *   fric_coeff[B,nb] / restitution[B,nb]. */
+int lcpb200_contact_geometry(int dtype, int B, int nb, int cap, const void* pos, const void* rad,
+                             const void* fric_coeff, const void* restitution, const int32_t* body1,
+                             const int32_t* body2, const int32_t* counts, void* normal, void* p1, void* p2,
+                             void* penetration, void* mu, void* restitution_c, void* stream);
+
 /* Contact-list -> dense LCP assembly for B scenes of nb bodies (3 dofs each,
  * n = 3 nb), nc contacts, fd = 2 friction directions (world.py:191-192),
  * m = nc (2 + fd). Structure-of-arrays inputs:

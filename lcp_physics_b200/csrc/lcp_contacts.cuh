@@ -85,6 +85,50 @@ __global__ void __launch_bounds__(NT) find_contacts_kernel(int B, int nb, int ca
   }
 }
 
+// Geometry of the selected pairs (contacts.py:69-77, world.py:144-151, :213-224), for callers that do not need
+// autograd through the contact generation: normal = (pos1 - pos2) / dist, penetration = r1 + r2 - dist,
+// p1 = -normal (r1 - pen / 2), p2 = normal (r2 - pen / 2), mu / restitution = mean of the two bodies'. Unused slots
+// (k >= counts[scene]) get the geometry of the padding pair and penetration = -1e30.
+template <typename T>
+__global__ void __launch_bounds__(NT) contact_geometry_kernel(int B, int nb, int cap, const T* __restrict__ pos,
+                                                              const T* __restrict__ rad, const T* __restrict__ fric,
+                                                              const T* __restrict__ rest, const int32_t* __restrict__ body1,
+                                                              const int32_t* __restrict__ body2,
+                                                              const int32_t* __restrict__ counts, T* __restrict__ normal,
+                                                              T* __restrict__ p1, T* __restrict__ p2, T* __restrict__ pen,
+                                                              T* __restrict__ mu, T* __restrict__ rest_c) {
+  const long long total = (long long)B * cap;
+  for (long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT) {
+    const int sc = (int)(t / cap), k = (int)(t - (long long)sc * cap);
+    const int i = body1[t], j = body2[t];
+    const T* P = pos + (size_t)sc * nb * 2;
+    const T* R = rad + (size_t)sc * nb;
+    const T dx = P[2 * i] - P[2 * j], dy = P[2 * i + 1] - P[2 * j + 1];
+    const T dist = sqrt(dx * dx + dy * dy);
+    const T r1 = R[i], r2 = R[j];
+    const T pn = r1 + r2 - dist;
+    const T nx = dx / dist, ny = dy / dist;
+    const T a1 = r1 - pn / 2, a2 = r2 - pn / 2;
+    normal[2 * t] = nx; normal[2 * t + 1] = ny;
+    p1[2 * t] = -nx * a1; p1[2 * t + 1] = -ny * a1;
+    p2[2 * t] = nx * a2; p2[2 * t + 1] = ny * a2;
+    pen[t] = k < counts[sc] ? pn : T(-1e30);
+    mu[t] = T(0.5) * (fric[(size_t)sc * nb + i] + fric[(size_t)sc * nb + j]);
+    rest_c[t] = T(0.5) * (rest[(size_t)sc * nb + i] + rest[(size_t)sc * nb + j]);
+  }
+}
+
+template <typename T>
+static void launch_contact_geometry(int B, int nb, int cap, const T* pos, const T* rad, const T* fric, const T* rest,
+                                    const int32_t* body1, const int32_t* body2, const int32_t* counts, T* normal, T* p1,
+                                    T* p2, T* pen, T* mu, T* rest_c, int num_sms, cudaStream_t st) {
+  const long long total = (long long)B * cap;
+  long long grid = (total + NT - 1) / NT;
+  if (grid > 8LL * num_sms) grid = 8LL * num_sms;
+  contact_geometry_kernel<T><<<(int)grid, NT, 0, st>>>(B, nb, cap, pos, rad, fric, rest, body1, body2, counts, normal, p1, p2,
+                                                        pen, mu, rest_c);
+}
+
 template <typename T>
 static void launch_find_contacts(int B, int nb, int cap, T eps, const T* pos, const T* rad, int32_t* body1,
                                  int32_t* body2, int32_t* counts, int num_sms, cudaStream_t st) {

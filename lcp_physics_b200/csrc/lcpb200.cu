@@ -915,6 +915,31 @@ extern "C" int lcpb200_find_contacts(int dtype, int B, int nb, int cap, double e
   return 0;
 }
 
+extern "C" int lcpb200_contact_geometry(int dtype, int B, int nb, int cap, const void* pos, const void* rad,
+                                        const void* fric, const void* rest, const int32_t* body1, const int32_t* body2,
+                                        const int32_t* counts, void* normal, void* p1, void* p2, void* pen, void* mu,
+                                        void* rest_c, void* stream) {
+  if (dtype != LCPB200_F32 && dtype != LCPB200_F64) return fail("bad dtype");
+  if (B < 0 || nb <= 0 || cap <= 0) return fail("contact_geometry: need B >= 0, nb > 0, cap > 0");
+  if (!pos || !rad || !fric || !rest || !body1 || !body2 || !counts || !normal || !p1 || !p2 || !pen || !mu || !rest_c)
+    return fail("contact_geometry: NULL argument");
+  if (B == 0) return 0;
+  int dev = 0, sms = 0;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LCPB200_F32)
+    cts::launch_contact_geometry<float>(B, nb, cap, (const float*)pos, (const float*)rad, (const float*)fric,
+                                        (const float*)rest, body1, body2, counts, (float*)normal, (float*)p1, (float*)p2,
+                                        (float*)pen, (float*)mu, (float*)rest_c, sms, st);
+  else
+    cts::launch_contact_geometry<double>(B, nb, cap, (const double*)pos, (const double*)rad, (const double*)fric,
+                                         (const double*)rest, body1, body2, counts, (double*)normal, (double*)p1,
+                                         (double*)p2, (double*)pen, (double*)mu, (double*)rest_c, sms, st);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int lcpb200_assemble(int dtype, int B, int nb, int nc, double dt, const void* mass, const void* inertia,
                                 const void* v, const void* fext, const void* normal, const void* p1,
                                 const void* p2, const int32_t* body1, const int32_t* body2, const void* mu,

@@ -106,6 +106,21 @@ class BatchedWorld:
                                                  ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
         if int(counts.max()) > cap:
             raise RuntimeError("BatchedWorld: a scene has %d contacts, capacity %d" % (int(counts.max()), cap))
+        self.c_b1, self.c_b2, self.counts = b1, b2, counts
+        needs_graph = torch.is_grad_enabled() and any(t.requires_grad for t in (self.p, self.rad, self.fric_coeff, self.restitution))
+        if not needs_graph:
+            # nothing to differentiate: the geometry of the selected pairs in one kernel as well
+            new = lambda *s_: torch.empty(B, cap, *s_, dtype=self.dtype, device=dev)
+            self.c_normal, self.c_p1, self.c_p2 = new(2), new(2), new(2)
+            self.c_pen, self.c_mu, self.c_rest = new(), new(), new()
+            with torch.cuda.device(dev):
+                _lib.check(lib.lcpb200_contact_geometry(
+                    _lib.dtype_code(self.dtype), B, self.nb, cap, _lib.ptr(pos_c), _lib.ptr(self.rad.detach().contiguous()),
+                    _lib.ptr(self.fric_coeff.detach().contiguous()), _lib.ptr(self.restitution.detach().contiguous()),
+                    _lib.ptr(b1), _lib.ptr(b2), _lib.ptr(counts),
+                    *[_lib.ptr(t) for t in (self.c_normal, self.c_p1, self.c_p2, self.c_pen, self.c_mu, self.c_rest)],
+                    ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            return
         i1, i2 = b1.long(), b2.long()
         take = lambda t, idx: torch.gather(t, 1, idx)
         d = torch.gather(pos, 1, i1.unsqueeze(2).expand(-1, -1, 2)) - torch.gather(pos, 1, i2.unsqueeze(2).expand(-1, -1, 2))

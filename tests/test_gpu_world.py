@@ -74,3 +74,27 @@ def test_find_contacts_reports_overflow():
     ic = make_ball_pile(2, nballs=40, cols=8, seed=1, gap=0.05)
     with pytest.raises(RuntimeError, match="capacity"):
         BatchedWorld(ic["pos"], ic["rad"], gravity=100.0, static=[0], contact_capacity=16)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_fused_contact_geometry_matches_torch_geometry(dtype):
+    """lcpb200_contact_geometry (used when nothing needs autograd) against the differentiable torch geometry of the
+    same selected pairs: normal, p1, p2, penetration, mu, restitution."""
+    from lcp_physics_b200.scenes import make_ball_pile
+    from lcp_physics_b200.world import BatchedWorld
+    ic = make_ball_pile(7, nballs=40, cols=8, seed=9, gap=0.05)
+    if dtype == torch.float32:
+        ic = {k: v.float() for k, v in ic.items()}
+    mk = lambda: BatchedWorld(ic["pos"], ic["rad"], vel=ic["vel"], mass=ic["mass"], restitution=ic["rest"],
+                              fric_coeff=ic["fric"], gravity=100.0, static=[0], contact_capacity=160)
+    a, b = mk(), mk()
+    b.p.requires_grad_(True)                     # forces the torch (autograd) path
+    b.find_contacts()
+    assert b.c_normal.requires_grad and not a.c_normal.requires_grad
+    assert torch.equal(a.counts, b.counts) and torch.equal(a.c_b1, b.c_b1) and torch.equal(a.c_b2, b.c_b2)
+    tol = 1e-13 if dtype == torch.float64 else 1e-5
+    valid = torch.arange(a.cap, device=a.device).unsqueeze(0) < a.counts.unsqueeze(1)
+    for name in ("c_normal", "c_p1", "c_p2", "c_pen", "c_mu", "c_rest"):
+        x, y = getattr(a, name), getattr(b, name).detach()
+        assert torch.allclose(x[valid], y[valid], rtol=tol, atol=tol * 20), name
+    assert bool((a.c_pen[~valid] < -1e29).all())
