@@ -783,9 +783,7 @@ __device__ __noinline__ void band_lu(const Ctx& c, BProf& pf) {
     LUPROF_LAP(BPH_STEP);
     // ---- entering row / column of this warp: loads now, stores after the update
     Entering en;
-#ifndef LCP_BAND_LATE_ENTER
     enter_load(en, Kb, KbT, Brow, Bcol, k0 + Wc + warp, Nbp, ldk, bw, lane);
-#endif
     LUPROF_LAP(BPH_WINV);
     // ---- trailing update C -= L21 U12 (rank 8) on the FP64 tensor pipe: the (na + BD)^2 region is cut into
     // 8 x 8 tiles (a tile's 8 rows / columns are consecutive window slots: s0, Wc and na are multiples of 8, so a
@@ -860,9 +858,6 @@ __device__ __noinline__ void band_lu(const Ctx& c, BProf& pf) {
       }
     }
     LUPROF_LAP(BPH_POST);
-#ifdef LCP_BAND_LATE_ENTER
-    enter_load(en, Kb, KbT, Brow, Bcol, k0 + Wc + warp, Nbp, ldk, bw, lane);
-#endif
     enter_store(en, win, k0 + Wc + warp, s0 + warp, k0 + PV, Nbp, Wc, LDW, bw, lane);
     __syncthreads();
     LUPROF_LAP(BPH_RHS);
