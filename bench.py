@@ -136,18 +136,20 @@ def use_all_host_threads():
     return torch.get_num_threads()
 
 
-def cpu_reference_leg(B_sample, dtype, seed, reps=1, cfg2=False):
-    """Oracle port of the reference CPU path (as-is semantics) on B_sample scenes: fwd+bwd (cfg3) or forward (cfg2)."""
+def cpu_reference_leg(B_sample, dtype, seed, reps=1, cfg2=False, unpack="loop"):
+    """Oracle port of the reference CPU path on B_sample scenes: fwd+bwd (cfg3) or forward (cfg2). unpack="loop": as-is
+    semantics (the reference's per-row Python pivot loop, util.py:86-90); "vec": the same arithmetic with that loop
+    vectorised over the batch (the "modern torch" restatement SURVEY.md section 8d asks to report next to it)."""
     from oracle import pdipm_oracle as po
     from lcp_physics_b200.scenes import make_scenes
     nb, nc, fd, e = (CFG2["nb"], CFG2["nc"], CFG2["fd"], CFG2["e"]) if cfg2 else (NB, NC, FD, NEQ)
     inp = make_scenes(B_sample, nb, nc, fd=fd, e=e, dtype=dtype, seed=seed)
     g = torch.randn(B_sample, 3 * nb, dtype=dtype, generator=torch.Generator().manual_seed(seed))
     small = tuple(t[:4] if t.dim() > 1 else t for t in inp)
-    po.lcp_backward(po.lcp_forward(*small, max_iter=MAX_ITER, unpack="loop"), g[:4])   # warm-up
+    po.lcp_backward(po.lcp_forward(*small, max_iter=MAX_ITER, unpack=unpack), g[:4])   # warm-up
     t0 = time.perf_counter()
     for _ in range(reps):
-        res = po.lcp_forward(*inp, max_iter=MAX_ITER, unpack="loop")
+        res = po.lcp_forward(*inp, max_iter=MAX_ITER, unpack=unpack)
         if not cfg2:
             po.lcp_backward(res, g)
     dt = (time.perf_counter() - t0) / reps
@@ -210,6 +212,7 @@ def run_reference(args, rank, world):
         cpu_reference_leg(Bs, rdt, 100 + k, cfg2=cfg2)
     dt = time.perf_counter() - t0
     val = Bs * args.steps / dt
+    vec_val, _ = cpu_reference_leg(Bs, rdt, 100, cfg2=cfg2, unpack="vec")
     line = {
         "impl": "reference", "metric": METRIC_CFG2 if cfg2 else METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -219,7 +222,10 @@ def run_reference(args, rank, world):
                    "note": "each step times a bounded sample of the workload (sample_batch scenes) on the host cores"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d scenes per step (of the %d-scene batch), %s, as-is reference "
-                                   "semantics incl. util.py:86-90 pivot loop" % (Bs, full_batch, "forward" if cfg2 else "fwd+bwd")},
+                                   "semantics incl. util.py:86-90 pivot loop" % (Bs, full_batch, "forward" if cfg2 else "fwd+bwd"),
+                         "vectorised_restatement_value": vec_val,
+                         "vectorised_note": "same arithmetic with the per-row Python pivot loop vectorised over the batch "
+                                            "(oracle unpack='vec'), one %d-scene sample" % Bs},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -469,6 +475,8 @@ def run_cfg4(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD_CFG4, "worlds_per_gpu": B, "global_worlds": world * B,
                        "parallelism": "replicas x%d (one scene does not shard)" % world,
                        "mean_contacts": float(torch.stack(ncs).mean()), "mean_pdipm_iters": float(torch.stack(its).mean()),
+                       "contacts_min_max_over_steps": [float(torch.stack(ncs).min()), float(torch.stack(ncs).max())],
+                       "n_m_e": [3 * (CFG4["nballs"] + 1), "4 x contacts", 3],
                        "l2": "working set per world (factors + band, ~8 MB) is L2 resident by design; inputs are 60 KB"},
             "kernel": {"name": "band_forward_kernel", "ms_per_launch": kernel_ms, "launches_per_step": 1,
                        "share_of_step": kernel_ms / (ms / args.steps), "half_bandwidth": bw, "order": N,
