@@ -33,3 +33,26 @@ def test_algorithmic_bytes_and_measured_traffic_helpers():
     t = bench.measured_traffic(4096)
     assert t is None or t > 1e9            # bytes per forward launch from the newest profiles/*_fwd_traffic.json
     assert bench.measured_traffic(2048) is None or abs(bench.measured_traffic(2048) * 2 - t) < 1.0
+
+
+def test_world_reference_arm_and_scene_generators():
+    """--config world reference arm (oracle world on the host) prints the contract line; the config-4 / world initial
+    conditions are piles in contact from step 0 (what the bench lines claim)."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "world",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert d["impl"] == "reference" and d["unit"] == "world-steps/s" and d["value"] > 0 and d["gpu_launches"] == 0
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle.world_oracle import OracleCircleWorld
+    ic = bench.world_initial(2, 0)
+    assert ic["pos"].shape == (2, 25, 2)
+    w = OracleCircleWorld(ic["pos"][1], ic["rad"][1], ic["vel"][1], ic["mass"][1], ic["rest"][1], ic["fric"][1],
+                          gravity=100.0, static=(0,), dt=1.0 / 30)
+    assert 40 <= len(w.contacts) <= 75                       # 24-ball pile: ~51 contacts, within BatchedWorld's default capacity
+    ic4 = bench.cfg4_initial(1, 0)
+    assert ic4["pos"].shape == (1, 513, 2) and float(ic4["rad"][0, 1]) == 10.0
+    # neighbours of the hexagonal pile are closer than eps = 0.1: in contact before the first step
+    d01 = (ic4["pos"][0, 1] - ic4["pos"][0, 2]).norm() - 20.0
+    assert 0.0 < float(d01) < 0.1
